@@ -1,0 +1,105 @@
+/* ubs_gnn.h — C ABI of the B200-native hetero-graph message-passing hot path of uav_bs_ctrl.
+ *
+ * Drop-in boundary: these entry points replace what the reference delegates to
+ * DGL 0.9.0 / PyTorch 1.12 from
+ *   - dglnn.GATv2Conv.forward          (call sites algos/madrqn/agents/gnn_agents.py:92-97,103-104,
+ *                                        algos/drqn/agents/gnn_agents.py:17-18,27)
+ *   - TarMAC.forward's edge ops         (algos/madrqn/agents/gnn_agents.py:261-266: apply_edges(u_dot_v),
+ *                                        edge_softmax, update_all(u_mul_e, sum))
+ *   - nn.GRUCell                        (gnn_agents.py:29,246,270; drqn gnn_agents.py:20,28)
+ * and are what a ctypes / pybind binding on the reference side would bind.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only; every pointer is a DEVICE pointer to fp32 / int32 / uint32 data
+ *     owned by the caller (PyTorch's caching allocator in our host code); nothing is allocated, freed or
+ *     retained past return; workspaces are caller-provided.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no device sync).
+ *   - return value 0 = success; non-zero = failure, message via ubs_last_error() (thread-local).
+ *   - graphs are CSR-by-destination: in-edges of dst v are slots [indptr[v], indptr[v+1]);
+ *     src_idx[slot] is the source node, or src_idx == NULL for the star layout (source id == slot id).
+ *   - feature index of (head k, channel d) is k*D + d (head-major, what `.view(N,-1)` flattens,
+ *     gnn_agents.py:103-104).
+ */
+#ifndef UBS_GNN_H_
+#define UBS_GNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBS_GNN_VERSION 100
+
+#if defined(__GNUC__)
+#define UBS_API __attribute__((visibility("default")))
+#else
+#define UBS_API
+#endif
+
+/* flags for ubs_gatv2_* */
+#define UBS_GAT_RESIDUAL 1 /* res_fc is a Linear(F_d, H) (always the case at the reference call sites) */
+#define UBS_GAT_RELU 2     /* activation=nn.ReLU() */
+
+UBS_API int ubs_version(void);
+UBS_API const char* ubs_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (bench "gpu_launches"). */
+UBS_API int64_t ubs_launch_count(void);
+UBS_API void ubs_reset_launch_count(void);
+
+/* ---- GATv2 relation, fused projection (F_s <= 4, F_d <= 2, H = heads*D in {32,64,128}) -----------------
+ * out[v, k, :] = act( sum_e alpha[e,k] * (W_src x_src[u_e] + b_src)[k,:] + W_res x_dst[v] + b_res )
+ * alpha = edge_softmax_by_dst( attn[k,:] . leaky_relu(W_src x_u + b_src + W_dst x_v + b_dst)[k,:] )
+ * smax / ssum (n_dst*heads each, may both be NULL for inference) receive the per-(dst,head) softmax max and
+ * denominator that the backward needs.                                                                     */
+UBS_API int ubs_gatv2_fwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                  const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                  const float* attn, const float* W_res, const float* b_res,
+                  float* out, float* smax, float* ssum,
+                  int64_t n_dst, int64_t n_edges, int F_s, int F_d, int heads, int D,
+                  float negative_slope, int flags, void* stream);
+
+/* Size in floats of the workspace ubs_gatv2_bwd needs (per-CTA partial parameter gradients). */
+UBS_API int64_t ubs_gatv2_bwd_workspace(int64_t n_dst, int F_s, int F_d, int heads, int D);
+
+/* Backward of ubs_gatv2_fwd.  grad_params is ONE flat buffer laid out as
+ *   [gW_src (H*F_s) | gb_src (H) | gW_dst (H*F_d) | gb_dst (H) | gattn (H) | gW_res (H*F_d) | gb_res (H)]
+ * and is overwritten (not accumulated).  grad_x_src (n_src*F_s) / grad_x_dst (n_dst*F_d) may be NULL when the
+ * observations are leaves (always the case in the env configs); when given, grad_x_src must be zero-filled by
+ * the caller if src_idx != NULL (several edges may share a source).  Deterministic: two-stage reduction.    */
+UBS_API int ubs_gatv2_bwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                  const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                  const float* attn, const float* W_res, const float* b_res,
+                  const float* out, const float* grad_out, const float* smax, const float* ssum,
+                  float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                  int64_t n_dst, int64_t n_edges, int64_t n_src, int F_s, int F_d, int heads, int D,
+                  float negative_slope, int flags, void* stream);
+
+/* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
+ * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
+ * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.
+ *   e[u->v] = <s_u, q_v> * scale ; a = softmax over in-edges of v ; c_v = sum_u a[u->v] * val_u
+ * s/q/val are row-strided views (ld_* in floats) so they may alias one (N, M+2K) projection buffer.
+ * alpha (N*block, dense per dst, 0 where no edge) is written for the backward.                              */
+UBS_API int ubs_block_attn_fwd(const float* s, int64_t ld_s, const float* q, int64_t ld_q, const float* val, int64_t ld_v,
+                       const uint32_t* mask, float* c, float* alpha,
+                       int64_t n_nodes, int block, int key_size, int msg_size, float scale, void* stream);
+
+/* ds_work: workspace of n_nodes*block floats. grad_s / grad_q / grad_val are row-strided like the inputs and are
+ * overwritten.                                                                                              */
+UBS_API int ubs_block_attn_bwd(const float* s, int64_t ld_s, const float* q, int64_t ld_q, const float* val, int64_t ld_v,
+                       const uint32_t* mask, const float* alpha, const float* grad_c,
+                       float* grad_s, int64_t ld_gs, float* grad_q, int64_t ld_gq, float* grad_val, int64_t ld_gv,
+                       float* ds_work, int64_t n_nodes, int block, int key_size, int msg_size, float scale,
+                       void* stream);
+
+/* ---- GRUCell gate math (nn.GRUCell, gate order r,z,n) given gi = W_ih x + b_ih, gh = W_hh h + b_hh --------- */
+UBS_API int ubs_gru_gates_fwd(const float* gi, const float* gh, const float* h, float* h_out, int64_t n, int H, void* stream);
+/* grad_gi, grad_gh: (n, 3H); grad_h_direct: (n, H) = grad_out * z (the part that does not go through W_hh). */
+UBS_API int ubs_gru_gates_bwd(const float* gi, const float* gh, const float* h, const float* grad_out,
+                      float* grad_gi, float* grad_gh, float* grad_h_direct, int64_t n, int H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBS_GNN_H_ */

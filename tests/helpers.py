@@ -75,3 +75,17 @@ def assert_close(a, b, rtol=1e-5, atol_scale=1e-6, what=""):
     bad = (a - b).abs() > atol + rtol * b.abs()
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{a.numel()} outside tol; max abs err "
                                  f"{float((a - b).abs().max()):.3e}, max ref {float(b.abs().max()):.3e}")
+
+
+def assert_as_accurate(a, ref32, ref64, what="", slack=4.0, floor_scale=2e-6, abs_floor=1e-9):
+    """Reduction-heavy results (parameter gradients sum thousands of cancelling terms): the kernel must be as
+    accurate against the fp64 oracle as the fp32 oracle itself is (x slack), with a floor of 2e-6 * max|ref|."""
+    a = a.detach().double().cpu().reshape(-1)
+    r32, r64 = ref32.detach().double().cpu().reshape(-1), ref64.detach().double().cpu().reshape(-1)
+    assert a.shape == r64.shape, f"{what}: shape mismatch"
+    if a.numel() == 0:
+        return
+    scale = float(r64.abs().max())
+    err_k, err_o = float((a - r64).abs().max()), float((r32 - r64).abs().max())
+    bound = max(slack * err_o, floor_scale * scale, abs_floor)
+    assert err_k <= bound, f"{what}: kernel err {err_k:.3e} vs fp64 > bound {bound:.3e} (fp32 oracle err {err_o:.3e}, scale {scale:.3e})"

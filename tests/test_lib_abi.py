@@ -1,0 +1,41 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ubs_gnn.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ubs_gnn.h")).read()
+    return sorted(set(re.findall(r"UBS_API\s+[\w\s\*]+?\b(ubs_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _header_symbols()
+    for s in ("ubs_version", "ubs_last_error", "ubs_gatv2_fwd", "ubs_gatv2_bwd", "ubs_block_attn_fwd",
+              "ubs_block_attn_bwd", "ubs_gru_gates_fwd", "ubs_gru_gates_bwd"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from uav_bs_ctrl_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in _header_symbols():
+        assert hasattr(lib, s), f"{s} declared in ubs_gnn.h but not exported"
+    assert set(_lib.exported_symbols()) == set(_header_symbols())
+    loaded = _lib.load()
+    assert loaded.ubs_version() == 100
+    assert loaded.ubs_last_error() is not None
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    """No CPU fallback: product modules refuse CPU tensors instead of silently running eager code."""
+    import torch as th
+    from uav_bs_ctrl_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.GRUGates.apply(th.zeros(2, 6), th.zeros(2, 6), th.zeros(2, 2))

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI in ``include/ubs_gnn.h`` (in-tree ``libubs_gnn.so``, sm_100a).
+
+There is no fallback: if the library is missing or a call fails, a ``RuntimeError`` is raised.  PyTorch is used
+only for device memory and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import torch as th
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libubs_gnn.so")
+_lib = None
+
+_F, _I, _U = C.c_void_p, C.c_void_p, C.c_void_p      # device pointers travel as void*
+_i64, _int, _flt, _ptr = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+_PROTOS = {
+    "ubs_version": (C.c_int, []),
+    "ubs_last_error": (C.c_char_p, []),
+    "ubs_launch_count": (_i64, []),
+    "ubs_reset_launch_count": (None, []),
+    "ubs_gatv2_fwd": (C.c_int, [_F, _F, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i64,
+                                _int, _int, _int, _int, _flt, _int, _ptr]),
+    "ubs_gatv2_bwd_workspace": (_i64, [_i64, _int, _int, _int, _int]),
+    "ubs_gatv2_bwd": (C.c_int, [_F, _F, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F,
+                                _i64, _i64, _i64, _int, _int, _int, _int, _flt, _int, _ptr]),
+    "ubs_block_attn_fwd": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _U, _F, _F, _i64, _int, _int, _int, _flt, _ptr]),
+    "ubs_block_attn_bwd": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _U, _F, _F, _F, _i64, _F, _i64, _F, _i64, _F,
+                                     _i64, _int, _int, _int, _flt, _ptr]),
+    "ubs_gru_gates_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _int, _ptr]),
+    "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite against the header)."""
+    return list(_PROTOS)
+
+
+def build(verbose: bool = False) -> str:
+    """Compiles ``csrc/*.cu`` for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"building libubs_gnn.so failed:\n{res.stdout[-4000:]}\n{res.stderr[-4000:]}")
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           f"(there is no CPU / eager fallback for the CUDA hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.ubs_version() != 100:
+        raise RuntimeError(f"libubs_gnn.so version mismatch: {lib.ubs_version()}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {load().ubs_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return th.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().ubs_launch_count())
+
+
+def reset_launch_count():
+    load().ubs_reset_launch_count()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("uav_bs_ctrl_b200 kernels run on CUDA tensors only (no CPU fallback); "
+                               "use oracle/ for CPU checks")

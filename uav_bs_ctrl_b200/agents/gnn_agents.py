@@ -1,0 +1,323 @@
+"""Agent modules of the hot path with the reference's constructor / forward signatures and ``state_dict`` keys.
+
+Mirrors reference ``algos/madrqn/agents/gnn_agents.py`` (``GnnAgent`` :12-56, ``DenseObservationEncoder`` :62-77,
+``GraphObservationEncoder`` :80-107, ``BaseComm`` :113-148, ``DiscreteComm`` :151-193, ``CommNet`` :196-229,
+``TarMAC`` :232-271, ``EdgeConv`` :274-299), ``algos/drqn/agents/gnn_agents.py`` (``GnnAgent`` :9-30) and DGL 0.9.0's
+``dglnn.GATv2Conv``, but the graph arithmetic runs in the sm_100a kernels behind
+``include/ubs_gnn.h`` (``ops.py``); DGL is not used.  ``learner._build_agent`` can instantiate these through
+``REGISTRY['gnn']`` unchanged.
+"""
+from __future__ import annotations
+
+import torch as th
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .dueling import DuelingLayer
+
+
+class GRUCell(nn.GRUCell):
+    """``nn.GRUCell`` parameters (``weight_ih, weight_hh, bias_ih, bias_hh``); gate math in ``ubs_gru_gates_*``."""
+
+    def forward(self, x, h):
+        return ops.gru_cell(x, h, self.weight_ih, self.weight_hh, self.bias_ih, self.bias_hh)
+
+
+class GATv2Conv(nn.Module):
+    """Drop-in for ``dglnn.GATv2Conv`` (DGL 0.9.0 signature, parameter names, init order).
+
+    ``forward(graph, (feat_src, feat_dst)) -> (N_dst, heads, out_feats)`` where ``graph`` is a relation view
+    (``g['seen']``).  The fused kernel covers the reference's shapes (``F_src <= 4``, ``F_dst <= 2``,
+    ``heads*out_feats in {32, 64, 128}``); other shapes raise — there is no silent eager fallback."""
+
+    def __init__(self, in_feats, out_feats, num_heads, feat_drop=0., attn_drop=0., negative_slope=0.2,
+                 residual=False, activation=None, allow_zero_in_degree=False, bias=True, share_weights=False):
+        super().__init__()
+        if feat_drop != 0. or attn_drop != 0.:
+            raise NotImplementedError("feat_drop / attn_drop are 0 at every reference call site")
+        self._num_heads = num_heads
+        self._in_src_feats, self._in_dst_feats = in_feats if isinstance(in_feats, tuple) else (in_feats, in_feats)
+        self._out_feats = out_feats
+        self._allow_zero_in_degree = allow_zero_in_degree
+        self._negative_slope = negative_slope
+        self.fc_src = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=bias)
+        if share_weights and not isinstance(in_feats, tuple):
+            self.fc_dst = self.fc_src
+        else:
+            self.fc_dst = nn.Linear(self._in_dst_feats, out_feats * num_heads, bias=bias)
+        self.attn = nn.Parameter(th.empty(1, num_heads, out_feats))
+        if residual:
+            if self._in_dst_feats != out_feats:
+                self.res_fc = nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=bias)
+            else:
+                raise NotImplementedError("identity residual (in_dst_feats == out_feats) never occurs on this path")
+        else:
+            self.register_buffer("res_fc", None)
+        self.activation = activation
+        self.share_weights, self.bias = share_weights, bias
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
+        if self.bias:
+            nn.init.constant_(self.fc_src.bias, 0)
+        if self.fc_dst is not self.fc_src:
+            nn.init.xavier_normal_(self.fc_dst.weight, gain=gain)
+            if self.bias:
+                nn.init.constant_(self.fc_dst.bias, 0)
+        nn.init.xavier_normal_(self.attn, gain=gain)
+        if isinstance(self.res_fc, nn.Linear):
+            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+            if self.bias:
+                nn.init.constant_(self.res_fc.bias, 0)
+
+    def forward(self, graph, feat, get_attention=False):
+        if get_attention:
+            raise NotImplementedError("get_attention=True is not used on this path")
+        h_src, h_dst = feat if isinstance(feat, tuple) else (feat, feat)
+        csr = graph.csr()
+        if not self._allow_zero_in_degree and csr.n_dst and int((csr.indptr[1:] == csr.indptr[:-1]).any()):
+            raise RuntimeError("There are 0-in-degree nodes in the graph; set allow_zero_in_degree=True")
+        relu = isinstance(self.activation, nn.ReLU) or self.activation in (F.relu, th.relu)
+        if self.activation is not None and not relu:
+            flags, post = 0, self.activation
+        else:
+            flags, post = (ops.GAT_RELU if relu else 0), None
+        has_res = isinstance(self.res_fc, nn.Linear)
+        flags |= ops.GAT_RESIDUAL if has_res else 0
+        if not ops.gatv2_fused_supported(self._in_src_feats, self._in_dst_feats, self._num_heads, self._out_feats,
+                                         self._negative_slope):
+            raise NotImplementedError(
+                f"GATv2Conv shape (F_src={self._in_src_feats}, F_dst={self._in_dst_feats}, heads={self._num_heads}, "
+                f"D={self._out_feats}) is outside the fused kernel's range")
+        out = ops.GATv2Fused.apply(h_src, h_dst, csr.indptr, csr.src_idx, self.fc_src.weight, self.fc_src.bias,
+                                   self.fc_dst.weight, self.fc_dst.bias, self.attn,
+                                   self.res_fc.weight if has_res else None, self.res_fc.bias if has_res else None,
+                                   self._num_heads, self._out_feats, self._negative_slope, flags)
+        out = out.view(-1, self._num_heads, self._out_feats)
+        return post(out) if post is not None else out
+
+
+# ============================================================================================== encoders
+class DenseObservationEncoder(nn.Module):
+    """MLP observation encoder (reference ``gnn_agents.py:62-77``)."""
+
+    def __init__(self, obs_shape, args):
+        super().__init__()
+        self._n_layers, self._hidden_size = args.n_layers, args.hidden_size
+        layers = [nn.Linear(obs_shape, self._hidden_size), nn.ReLU()]
+        for _ in range(self._n_layers - 1):
+            layers += [nn.Linear(self._hidden_size, self._hidden_size), nn.ReLU()]
+        self.enc = nn.Sequential(*layers)
+
+    def forward(self, g, x):
+        return self.enc(x["agent"])
+
+
+class GraphObservationEncoder(nn.Module):
+    """Heterogeneous graph observation encoder (reference ``gnn_agents.py:80-107``): one GATv2 per relation
+    (``seen``: gt→agent, ``near``: ubs→agent), head-major flatten, concat, ``Linear(2H, H) + ReLU``."""
+
+    def __init__(self, obs_shape, args):
+        super().__init__()
+        n_heads, out_feats = args.n_heads, args.hidden_size
+        assert out_feats % n_heads == 0, "out_feats cannot be divided by n_heads in GraphObservationLayer."
+        feats_per_head = out_feats // n_heads
+        self.f_conv = nn.ModuleDict({
+            "seen": GATv2Conv((obs_shape["gt"], obs_shape["agent"]), feats_per_head, n_heads, residual=True,
+                              allow_zero_in_degree=True, activation=nn.ReLU()),
+            "near": GATv2Conv((obs_shape["ubs"], obs_shape["agent"]), feats_per_head, n_heads, residual=True,
+                              allow_zero_in_degree=True, activation=nn.ReLU()),
+        })
+        self.f_aggr = nn.Sequential(nn.Linear(len(self.f_conv) * out_feats, out_feats), nn.ReLU())
+
+    def forward(self, g, x):
+        n = g.num_nodes("agent")
+        x_gt = self.f_conv["seen"](g["seen"], (x["gt"], x["agent"])).view(n, -1)
+        x_ubs = self.f_conv["near"](g["near"], (x["ubs"], x["agent"])).view(n, -1)
+        return self.f_aggr(th.cat((x_gt, x_ubs), 1))
+
+
+# ============================================================================================== comm protocols
+def _mean_by_dst(g, msg, n):
+    _, dst = g.edges()
+    out = th.zeros((n,) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device).index_add_(0, dst, msg)
+    deg = th.bincount(dst, minlength=n).clamp_(min=1).to(msg.dtype)
+    return out / deg.unsqueeze(1)
+
+
+class TarMAC(nn.Module):
+    """TarMAC targeted communication (reference ``gnn_agents.py:232-271``).
+
+    Per round: ``[v|s|q] = W_vsq [x ‖ h.detach()]`` (one library GEMM), block attention kernel
+    (``e = <s_u, q_v> / key_size``, softmax over in-edges, ``c_v = Σ a v_u``), then ``GRUCell([x ‖ c], h)``."""
+
+    def __init__(self, args):
+        super().__init__()
+        self._hidden_size, self._msg_size = args.hidden_size, args.msg_size
+        self._key_size, self._n_rounds = args.key_size, args.n_rounds
+        self.f_val = nn.Linear(2 * self._hidden_size, self._msg_size)
+        self.f_sign = nn.Linear(2 * self._hidden_size, self._key_size)
+        self.f_que = nn.Linear(2 * self._hidden_size, self._key_size)
+        self.f_udt = GRUCell(self._hidden_size + self._msg_size, self._hidden_size)
+
+    def forward(self, g, x, h):
+        blk = g.block_mask()
+        if blk is None:
+            raise NotImplementedError("TarMAC needs a batch of equally sized comm graphs with <= 32 agents each")
+        block, mask = blk
+        K, M = self._key_size, self._msg_size
+        w = th.cat((self.f_val.weight, self.f_sign.weight, self.f_que.weight), 0)
+        b = th.cat((self.f_val.bias, self.f_sign.bias, self.f_que.bias), 0)
+        for _ in range(self._n_rounds):
+            inputs = th.cat((x, h.detach()), 1)
+            vsq = th.addmm(b, inputs, w.t())
+            c = ops.BlockAttention.apply(vsq, mask, block, K, M, 1.0 / K)
+            h = self.f_udt(th.cat((x, c), 1), h)
+        return h
+
+
+class BaseComm(nn.Module):
+    """Reference ``gnn_agents.py:113-148``: message ``f_msg([x_u ‖ h_u.detach()])``, mean over in-edges, GRU."""
+
+    def __init__(self, args):
+        super().__init__()
+        self._hidden_size, self._msg_size = args.hidden_size, args.msg_size
+        self.f_msg = nn.Linear(2 * self._hidden_size, self._msg_size)
+        self.f_udt = GRUCell(self._hidden_size + self._msg_size, self._hidden_size)
+
+    def forward(self, g, x, h):
+        if g.number_of_edges() == 0:
+            c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
+        else:
+            src, _ = g.edges()
+            c = _mean_by_dst(g, self.f_msg(th.cat((x, h.detach()), 1)).index_select(0, src), x.shape[0])
+        return self.f_udt(th.cat((x, c), 1), h)
+
+
+class DiscreteComm(nn.Module):
+    """Reference ``gnn_agents.py:151-193``: 2-digit one-hot bits via hard Gumbel-softmax (tau=0.5) on every edge,
+    element-wise OR (max) over in-edges, ``f_dec``, GRU.  Noise comes from the torch RNG, per edge, as in the
+    reference's edge UDF."""
+
+    def __init__(self, args):
+        super().__init__()
+        self._hidden_size, self._msg_size = args.hidden_size, args.msg_size
+        self.f_enc = nn.Linear(2 * self._hidden_size, 2 * self._msg_size)
+        self.f_dec = nn.Linear(2 * self._msg_size, 2 * self._msg_size)
+        self.f_udt = GRUCell(self._hidden_size + 2 * self._msg_size, self._hidden_size)
+
+    def forward(self, g, x, h):
+        n = x.shape[0]
+        if g.number_of_edges() == 0:
+            c = th.zeros(n, 2 * self._msg_size, device=x.device)
+        else:
+            src, dst = g.edges()
+            logits = self.f_enc(th.cat((x, h.detach()), 1).index_select(0, src))
+            m = F.gumbel_softmax(logits.view(-1, self._msg_size, 2), tau=0.5, hard=True).flatten(1)
+            idx = dst.view(-1, 1).expand_as(m)
+            c = th.zeros(n, m.shape[1], dtype=m.dtype, device=m.device).scatter_reduce(0, idx, m, "amax",
+                                                                                       include_self=False)
+        return self.f_udt(th.cat((x, self.f_dec(c)), 1), h)
+
+
+class CommNet(nn.Module):
+    """Reference ``gnn_agents.py:196-229``: mean of neighbours' detached hidden states, skip connection."""
+
+    def __init__(self, args):
+        super().__init__()
+        self._hidden_size, self._n_rounds = args.hidden_size, args.n_rounds
+        self.c_mod = nn.Linear(self._hidden_size, self._hidden_size)
+        self.f_mod = GRUCell(self._hidden_size, self._hidden_size)
+
+    def forward(self, g, x, h):
+        for _ in range(self._n_rounds):
+            if g.number_of_edges() == 0:
+                c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
+            else:
+                src, _ = g.edges()
+                c = _mean_by_dst(g, h.detach().index_select(0, src), x.shape[0])
+            h = self.f_mod(x + self.c_mod(c), h)
+        return h
+
+
+class EdgeConv(nn.Module):
+    """Reference ``gnn_agents.py:274-299``: message ``f_msg([x_u ‖ h_u ‖ x_v ‖ h_v])`` (h detached), mean, GRU."""
+
+    def __init__(self, args):
+        super().__init__()
+        self._hidden_size, self._msg_size, self._n_rounds = args.hidden_size, args.msg_size, args.n_rounds
+        self.f_msg = nn.Linear(4 * self._hidden_size, self._msg_size)
+        self.f_udt = GRUCell(self._hidden_size + self._msg_size, self._hidden_size)
+
+    def forward(self, g, x, h):
+        for _ in range(self._n_rounds):
+            if g.number_of_edges() == 0:
+                c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
+            else:
+                src, dst = g.edges()
+                xh = th.cat((x, h.detach()), 1)
+                c = _mean_by_dst(g, self.f_msg(th.cat((xh.index_select(0, src), xh.index_select(0, dst)), 1)), x.shape[0])
+            h = self.f_udt(th.cat((x, c), 1), h)
+        return h
+
+
+# ============================================================================================== agents
+class GnnAgent(nn.Module):
+    """Recurrent agent with graph observation encoder and comm protocol (reference ``gnn_agents.py:12-56``)."""
+
+    def __init__(self, obs_shape, n_actions, args):
+        super().__init__()
+        self._hidden_size = args.hidden_size
+        self._comm_protocol = args.c
+        if isinstance(obs_shape, int):
+            self.enc = DenseObservationEncoder(obs_shape, args)
+        elif isinstance(obs_shape, dict):
+            self.enc = GraphObservationEncoder(obs_shape, args)
+        if self._comm_protocol is None:
+            self.rnn = GRUCell(self._hidden_size, self._hidden_size)
+        elif self._comm_protocol == "base":
+            self.f_comm = BaseComm(args)
+        elif self._comm_protocol == "disc":
+            self.f_comm = DiscreteComm(args)
+        elif self._comm_protocol == "commnet":
+            self.f_comm = CommNet(args)
+        elif self._comm_protocol == "tarmac":
+            self.f_comm = TarMAC(args)
+        elif self._comm_protocol == "econv":
+            self.f_comm = EdgeConv(args)
+        else:
+            raise KeyError("Unsupported communication scheme.")
+        self.f_out = DuelingLayer(self._hidden_size, n_actions) if args.dueling else nn.Linear(self._hidden_size, n_actions)
+
+    def init_hidden(self):
+        return th.zeros(1, self._hidden_size)
+
+    def forward(self, g, h):
+        x = self.enc(g, g.ndata["feat"]).view(g.num_nodes("agent"), -1)
+        h = self.f_comm(g["talk"], x, h) if self._comm_protocol is not None else self.rnn(x, h)
+        return self.f_out(h), h
+
+
+class DrqnGnnAgent(nn.Module):
+    """Single-UBS agent (reference ``algos/drqn/agents/gnn_agents.py:9-30``): one GATv2 (gt→agent), GRU, Linear."""
+
+    def __init__(self, obs_shape, n_actions, args):
+        super().__init__()
+        self._hidden_size, self._n_heads = args.hidden_size, args.n_heads
+        feats_per_head = self._hidden_size // self._n_heads
+        self.enc = GATv2Conv((obs_shape["gt"], obs_shape["agent"]), feats_per_head, self._n_heads, residual=True,
+                             allow_zero_in_degree=True, activation=nn.ReLU())
+        self.rnn = GRUCell(self._hidden_size, self._hidden_size)
+        self.f_out = nn.Linear(self._hidden_size, n_actions)
+
+    def init_hidden(self):
+        return th.zeros(1, self._hidden_size)
+
+    def forward(self, g, h):
+        rel = g[g.canonical_etypes[0]]
+        x = self.enc(rel, (g.nodes["gt"].data["feat"], g.nodes["agent"].data["feat"])).flatten(start_dim=1)
+        h = self.rnn(x, h)
+        return self.f_out(h), h

@@ -48,16 +48,9 @@ def build_obs_graph_batch(agent_obs: th.Tensor, gt_obs: th.Tensor, ubs_obs: th.T
     x_gt, ip_gt, _ = _star(gt_obs[..., 0].reshape(N, -1) == 1, gt_obs[..., 1:].reshape(N, gt_obs.shape[2], -1), N)
     x_ubs, ip_ubs, _ = _star(ubs_obs[..., 0].reshape(N, -1) == 1, ubs_obs[..., 1:].reshape(N, ubs_obs.shape[2], -1), N)
     E_gt, E_ubs = x_gt.shape[0], x_ubs.shape[0]
-    ar = th.arange(N, device=dev)
-
-    def star_edges(ip, E):
-        deg = (ip[1:] - ip[:-1]).to(th.int64)
-        return th.arange(E, device=dev), th.repeat_interleave(ar, deg)
-
     src, dst, csr = {}, {}, {}
     c_seen, c_near, c_talk = OBS_CETS[1], OBS_CETS[2], OBS_CETS[0]
-    src[c_seen], dst[c_seen] = star_edges(ip_gt, E_gt)
-    src[c_near], dst[c_near] = star_edges(ip_ubs, E_ubs)
+    src[c_seen] = dst[c_seen] = src[c_near] = dst[c_near] = None    # star layout: edge lists derive from the CSR
     csr[c_seen] = RelCSR(ip_gt, None, None, E_gt, N, E_gt)
     csr[c_near] = RelCSR(ip_ubs, None, None, E_ubs, N, E_ubs)
     if comm_adj is None:
@@ -68,9 +61,7 @@ def build_obs_graph_batch(agent_obs: th.Tensor, gt_obs: th.Tensor, ubs_obs: th.T
         bne_talk = [0] * B
     else:
         adj = comm_adj.to(th.bool)
-        b, i, j = th.nonzero(adj, as_tuple=True)                    # reference edge order (env, src, dst)
-        src[c_talk], dst[c_talk] = b * U + i, b * U + j
-        E_t = int(b.numel())
+        src[c_talk] = dst[c_talk] = None                            # (env, src, dst) order is rebuilt from eid
         adj_t = adj.transpose(1, 2)                                   # [b, dst, src]
         bt, jt, it = th.nonzero(adj_t, as_tuple=True)                 # CSR slot order (env, dst, src)
         indeg = adj_t.sum(-1).flatten()
@@ -78,7 +69,12 @@ def build_obs_graph_batch(agent_obs: th.Tensor, gt_obs: th.Tensor, ubs_obs: th.T
         th.cumsum(indeg, 0, out=ip[1:])
         edge_id = (th.cumsum(adj.flatten().to(th.int64), 0) - 1).view(B, U, U)
         eid = edge_id.transpose(1, 2)[adj_t]
-        csr[c_talk] = RelCSR(ip.to(th.int32), (bt * U + it).to(th.int32), eid, N, N, E_t)
+        mask = None
+        if U <= 32:
+            mask = (adj.to(th.int64) << th.arange(U, device=dev).view(1, U, 1)).sum(1).flatten().to(th.int32)
+        E_t = int(bt.numel())
+        csr[c_talk] = RelCSR(ip.to(th.int32), (bt * U + it).to(th.int32), eid, N, N, E_t,
+                             U if U <= 32 else None, mask)
         bne_talk = adj.sum((1, 2)).tolist()
     per_env_gt = (ip_gt[U::U] - ip_gt[:-1:U]).tolist() if B else []
     per_env_ubs = (ip_ubs[U::U] - ip_ubs[:-1:U]).tolist() if B else []

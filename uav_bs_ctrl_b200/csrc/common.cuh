@@ -1,0 +1,60 @@
+// Shared helpers for the ubs_gnn kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math_constants.h>
+#include <atomic>
+
+namespace ubs {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// reductions inside aligned groups of G lanes (G power of two <= 32)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace ubs
+
+#define UBS_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            ubs::set_error(__VA_ARGS__);  \
+            return 2;                     \
+        }                                 \
+    } while (0)

@@ -1,0 +1,520 @@
+// Fused GATv2 relation kernels (forward + backward) for small source/destination feature widths.
+//
+// Replaces what the reference delegates to dglnn.GATv2Conv (call sites
+// algos/madrqn/agents/gnn_agents.py:92-97,103-104; algos/drqn/agents/gnn_agents.py:17-18,27), i.e. DGL's
+// fc_src/fc_dst GEMMs + gSDDMM(u_add_v) + leaky_relu + (e*attn).sum + edge_softmax (5 kernels) + gSpMM(u_mul_e,sum)
+// + res_fc + ReLU, with ONE pass over the edges.
+//
+// Design notes:
+//  * F_s <= 4 and F_d <= 2 in the env configs, so el = W_src x_u + b_src is never materialised: it is recomputed
+//    in registers from the 8..16-byte source row.  The aggregation is linear in x, so the per-edge weighted sum
+//    runs on the RAW source row (F_s values per head) and is projected once per destination:
+//        ft[v,k,:] = W_src[k] (sum_e alpha[e,k] x_e) + b_src[k]
+//  * forward: a group of GS lanes owns one destination, one EDGE per lane; the H score channels are looped with
+//    the weights broadcast from shared memory; online softmax per lane, merged across the group at the end.
+//    Star layout => consecutive lanes read consecutive 16-byte rows: fully coalesced, no index array at all.
+//  * backward: one warp per destination, lanes own CPL = H/32 channels so every parameter-gradient accumulator
+//    lives in a register for the whole kernel; per-CTA partials go to a workspace and are summed by a second
+//    kernel in a fixed order (deterministic; no atomics on the parameter gradients).
+#include "common.cuh"
+#include "../../include/ubs_gnn.h"
+
+namespace ubs {
+
+struct GatArgs {
+    const float* x_src; const float* x_dst; const int* indptr; const int* src_idx;
+    const float* W_src; const float* b_src; const float* W_dst; const float* b_dst;
+    const float* attn; const float* W_res; const float* b_res;
+    float* out; float* smax; float* ssum;
+    // backward only
+    const float* grad_out; const float* out_in; const float* smax_in; const float* ssum_in;
+    float* partial; float* grad_x_src; float* grad_x_dst;
+    int n_dst; int F_d; int D; float slope; int flags;
+};
+
+template <int FS>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, size_t row, float (&x)[FS]) {
+    if constexpr (FS == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p) + row);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else if constexpr (FS == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p) + row);
+        x[0] = t.x; x[1] = t.y;
+    } else {
+#pragma unroll
+        for (int f = 0; f < FS; ++f) x[f] = __ldg(p + row * FS + f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int FS, int HEADS, int GS>
+__global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
+    constexpr int GPW = 32 / GS;           // destination groups per warp
+    constexpr int GPB = 256 / GS;          // groups per block
+    const int D = a.D, H = HEADS * D;
+    extern __shared__ float4 smem4[];
+    float4* wA = smem4;                    // [H] W_src row (zero padded to 4)
+    float4* wR = wA + H;                   // [H] {W_res[0], W_res[1], b_res, b_src}
+    float4* wD = wR + H;                   // [H] {W_dst[0], W_dst[1], b_src + b_dst, attn}
+    float* cbase = reinterpret_cast<float*>(wD + H);
+    const int cstride = 2 * H + 2;         // +2: groups of one warp hit different banks
+    const int tid = threadIdx.x;
+    for (int ch = tid; ch < H; ch += 256) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < FS; ++f) w[f] = a.W_src[ch * FS + f];
+        wA[ch] = make_float4(w[0], w[1], w[2], w[3]);
+        const float bs = a.b_src ? a.b_src[ch] : 0.f;
+        const float bd = a.b_dst ? a.b_dst[ch] : 0.f;
+        float r0 = 0.f, r1 = 0.f, rb = 0.f;
+        if (a.flags & UBS_GAT_RESIDUAL) {
+            r0 = a.W_res[ch * a.F_d];
+            r1 = a.F_d > 1 ? a.W_res[ch * a.F_d + 1] : 0.f;
+            rb = a.b_res ? a.b_res[ch] : 0.f;
+        }
+        wR[ch] = make_float4(r0, r1, rb, bs);
+        wD[ch] = make_float4(a.W_dst[ch * a.F_d], a.F_d > 1 ? a.W_dst[ch * a.F_d + 1] : 0.f, bs + bd, a.attn[ch]);
+    }
+    __syncthreads();
+
+    const int li = tid % GS;                               // lane inside the group
+    const int grp_in_block = tid / GS;
+    float2* cbuf = reinterpret_cast<float2*>(cbase + grp_in_block * cstride);
+    const int warp_first = (blockIdx.x * GPB) + (tid / 32) * GPW;
+    const int stride = gridDim.x * GPB;
+    const float slope = a.slope;
+    const bool relu = a.flags & UBS_GAT_RELU, has_res = a.flags & UBS_GAT_RESIDUAL;
+
+    for (int base = warp_first; base < a.n_dst; base += stride) {
+        const int v = base + (tid % 32) / GS;
+        const bool active = v < a.n_dst;
+        int beg = 0, end = 0;
+        float xv0 = 0.f, xv1 = 0.f;
+        if (active) {
+            beg = __ldg(a.indptr + v);
+            end = __ldg(a.indptr + v + 1);
+            xv0 = __ldg(a.x_dst + (size_t)v * a.F_d);
+            xv1 = a.F_d > 1 ? __ldg(a.x_dst + (size_t)v * a.F_d + 1) : 0.f;
+        }
+        // destination part of the score pre-activation, shared by all edges of v
+        for (int ch = li; ch < H; ch += GS) {
+            const float4 w = wD[ch];
+            cbuf[ch] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
+        }
+        __syncwarp();
+
+        float m[HEADS], l[HEADS], acc[HEADS][FS];
+#pragma unroll
+        for (int k = 0; k < HEADS; ++k) {
+            m[k] = -CUDART_INF_F; l[k] = 0.f;
+#pragma unroll
+            for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
+        }
+        for (int e = beg + li; e < end; e += GS) {
+            const size_t u = a.src_idx ? (size_t)__ldg(a.src_idx + e) : (size_t)e;
+            float x[FS];
+            load_row<FS>(a.x_src, u, x);
+#pragma unroll
+            for (int k = 0; k < HEADS; ++k) {
+                const float4* wk = wA + k * D;
+                const float2* ck = cbuf + k * D;
+                float s = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < D; ++d) {
+                    const float4 w = wk[d];
+                    const float2 c = ck[d];
+                    float z = c.x;
+                    z = fmaf(w.x, x[0], z);
+                    if constexpr (FS > 1) z = fmaf(w.y, x[1], z);
+                    if constexpr (FS > 2) z = fmaf(w.z, x[2], z);
+                    if constexpr (FS > 3) z = fmaf(w.w, x[3], z);
+                    const float y = fmaxf(z, slope * z);        // leaky_relu for 0 <= slope <= 1
+                    s = fmaf(c.y, y, s);
+                }
+                const float mn = fmaxf(m[k], s);
+                const float sc = expf(m[k] - mn);
+                const float p = expf(s - mn);
+                l[k] = fmaf(l[k], sc, p);
+#pragma unroll
+                for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[f]);
+                m[k] = mn;
+            }
+        }
+        // merge the per-lane online-softmax states of the group
+#pragma unroll
+        for (int k = 0; k < HEADS; ++k) {
+            const float M = group_max<GS>(m[k]);
+            const float sc = (m[k] == -CUDART_INF_F) ? 0.f : expf(m[k] - M);
+            l[k] = group_sum<GS>(l[k] * sc);
+#pragma unroll
+            for (int f = 0; f < FS; ++f) acc[k][f] = group_sum<GS>(acc[k][f] * sc);
+            m[k] = M;
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < HEADS; ++k) {
+                const float inv = l[k] > 0.f ? 1.0f / l[k] : 0.f;
+                for (int d = li; d < D; d += GS) {
+                    const int ch = k * D + d;
+                    const float4 w = wA[ch];
+                    const float4 r = wR[ch];
+                    float o = 0.f;
+                    if (l[k] > 0.f) {
+                        float t = w.x * acc[k][0];
+                        if constexpr (FS > 1) t = fmaf(w.y, acc[k][1], t);
+                        if constexpr (FS > 2) t = fmaf(w.z, acc[k][2], t);
+                        if constexpr (FS > 3) t = fmaf(w.w, acc[k][3], t);
+                        o = fmaf(t, inv, r.w);
+                    }
+                    if (has_res) o += fmaf(r.y, xv1, fmaf(r.x, xv0, r.z));
+                    if (relu) o = fmaxf(o, 0.f);
+                    a.out[(size_t)v * H + ch] = o;
+                }
+                if (li == 0 && a.smax != nullptr) {
+                    a.smax[(size_t)v * HEADS + k] = l[k] > 0.f ? m[k] : 0.f;
+                    a.ssum[(size_t)v * HEADS + k] = l[k];
+                }
+            }
+        }
+        __syncwarp();   // cbuf is rewritten by the next destination
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__host__ __device__ inline int gat_param_count(int H, int FS, int FD) { return H * (FS + 2 * FD + 4); }
+
+template <int FS, int CPL, int HEADS>
+__global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
+    constexpr int H = 32 * CPL, D = H / HEADS, LPH = 32 / HEADS;
+    static_assert(D % CPL == 0, "a lane's channels must stay inside one head");
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int head = (lane * CPL) / D;
+    const int FD = a.F_d;
+    const bool relu = a.flags & UBS_GAT_RELU, has_res = a.flags & UBS_GAT_RESIDUAL;
+    const float slope = a.slope;
+    __shared__ float4 xs[4][32];
+    __shared__ float red[H * (4 + 2 * 2 + 4)];
+
+    float ws[CPL][FS], wd[CPL][2], wr[CPL][2], bsum[CPL], bs[CPL], brr[CPL], at[CPL];
+    float g_ws[CPL][FS], g_wd[CPL][2], g_wr[CPL][2], g_bsd[CPL], g_bsm[CPL], g_br[CPL], g_at[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int ch = lane * CPL + j;
+#pragma unroll
+        for (int f = 0; f < FS; ++f) { ws[j][f] = a.W_src[ch * FS + f]; g_ws[j][f] = 0.f; }
+        wd[j][0] = a.W_dst[ch * FD]; wd[j][1] = FD > 1 ? a.W_dst[ch * FD + 1] : 0.f;
+        wr[j][0] = has_res ? a.W_res[ch * FD] : 0.f;
+        wr[j][1] = (has_res && FD > 1) ? a.W_res[ch * FD + 1] : 0.f;
+        brr[j] = (has_res && a.b_res) ? a.b_res[ch] : 0.f;
+        bs[j] = a.b_src ? a.b_src[ch] : 0.f;
+        bsum[j] = bs[j] + (a.b_dst ? a.b_dst[ch] : 0.f);
+        at[j] = a.attn[ch];
+        g_wd[j][0] = g_wd[j][1] = g_wr[j][0] = g_wr[j][1] = 0.f;
+        g_bsd[j] = g_bsm[j] = g_br[j] = g_at[j] = 0.f;
+    }
+
+    const int total_warps = gridDim.x * 4;
+    for (int v = blockIdx.x * 4 + warp; v < a.n_dst; v += total_warps) {
+        const int beg = __ldg(a.indptr + v), end = __ldg(a.indptr + v + 1);
+        const float xv0 = __ldg(a.x_dst + (size_t)v * FD);
+        const float xv1 = FD > 1 ? __ldg(a.x_dst + (size_t)v * FD + 1) : 0.f;
+        float gp[CPL], ft[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const size_t idx = (size_t)v * H + lane * CPL + j;
+            const float go = __ldg(a.grad_out + idx), oo = __ldg(a.out_in + idx);
+            gp[j] = (relu && !(oo > 0.f)) ? 0.f : go;
+            const float res = has_res ? fmaf(wr[j][1], xv1, fmaf(wr[j][0], xv0, brr[j])) : 0.f;
+            ft[j] = oo - res;                                   // only used where gp != 0
+            g_wr[j][0] = fmaf(gp[j], xv0, g_wr[j][0]);
+            g_wr[j][1] = fmaf(gp[j], xv1, g_wr[j][1]);
+            g_br[j] += gp[j];
+        }
+        float sdz[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) sdz[j] = 0.f;
+        if (end > beg) {                                        // warp-uniform
+            float dotp = 0.f, qk = 0.f, pk[FS];
+#pragma unroll
+            for (int f = 0; f < FS; ++f) pk[f] = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                dotp = fmaf(gp[j], ft[j], dotp);
+                qk = fmaf(gp[j], bs[j], qk);
+#pragma unroll
+                for (int f = 0; f < FS; ++f) pk[f] = fmaf(gp[j], ws[j][f], pk[f]);
+            }
+            dotp = group_sum<LPH>(dotp);
+            qk = group_sum<LPH>(qk);
+#pragma unroll
+            for (int f = 0; f < FS; ++f) pk[f] = group_sum<LPH>(pk[f]);
+            const float Mx = __ldg(a.smax_in + (size_t)v * HEADS + head);
+            const float invL = 1.0f / __ldg(a.ssum_in + (size_t)v * HEADS + head);
+            float c[CPL], abar[FS];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) c[j] = fmaf(wd[j][1], xv1, fmaf(wd[j][0], xv0, bsum[j]));
+#pragma unroll
+            for (int f = 0; f < FS; ++f) abar[f] = 0.f;
+
+            for (int e0 = beg; e0 < end; e0 += 32) {
+                const int cnt = min(32, end - e0);
+                int u_lane = 0;
+                if (lane < cnt) {
+                    u_lane = a.src_idx ? __ldg(a.src_idx + e0 + lane) : (e0 + lane);
+                    float xr[FS];
+                    load_row<FS>(a.x_src, (size_t)u_lane, xr);
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    t.x = xr[0];
+                    if constexpr (FS > 1) t.y = xr[1];
+                    if constexpr (FS > 2) t.z = xr[2];
+                    if constexpr (FS > 3) t.w = xr[3];
+                    xs[warp][lane] = t;
+                }
+                __syncwarp();
+                for (int i = 0; i < cnt; ++i) {
+                    const float4 t = xs[warp][i];
+                    const float x[4] = {t.x, t.y, t.z, t.w};
+                    float z[CPL], y[CPL], sp = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        float zz = c[j];
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) zz = fmaf(ws[j][f], x[f], zz);
+                        z[j] = zz;
+                        y[j] = fmaxf(zz, slope * zz);
+                        sp = fmaf(at[j], y[j], sp);
+                    }
+                    const float s = group_sum<LPH>(sp);
+                    const float alpha = expf(s - Mx) * invL;
+                    float da = qk;
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) da = fmaf(pk[f], x[f], da);
+                    const float ds = alpha * (da - dotp);
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) abar[f] = fmaf(alpha, x[f], abar[f]);
+                    float gxs[FS];
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) gxs[f] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        g_at[j] = fmaf(ds, y[j], g_at[j]);
+                        const float dz = ds * at[j] * (z[j] > 0.f ? 1.0f : slope);
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) g_ws[j][f] = fmaf(dz, x[f], g_ws[j][f]);
+                        sdz[j] += dz;
+                        if (a.grad_x_src != nullptr) {
+                            const float t2 = fmaf(alpha, gp[j], dz);
+#pragma unroll
+                            for (int f = 0; f < FS; ++f) gxs[f] = fmaf(t2, ws[j][f], gxs[f]);
+                        }
+                    }
+                    if (a.grad_x_src != nullptr) {               // warp-uniform
+                        const int u = __shfl_sync(0xffffffffu, u_lane, i);
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) {
+                            const float tot = warp_sum(gxs[f]);
+                            if (lane == 0) {
+                                if (a.src_idx) atomicAdd(a.grad_x_src + (size_t)u * FS + f, tot);
+                                else a.grad_x_src[(size_t)u * FS + f] = tot;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+#pragma unroll
+                for (int f = 0; f < FS; ++f) g_ws[j][f] = fmaf(gp[j], abar[f], g_ws[j][f]);   // message path
+                g_bsm[j] += gp[j];                                                            // sum_e alpha = 1
+                g_wd[j][0] = fmaf(sdz[j], xv0, g_wd[j][0]);
+                g_wd[j][1] = fmaf(sdz[j], xv1, g_wd[j][1]);
+                g_bsd[j] += sdz[j];
+            }
+        }
+        if (a.grad_x_dst != nullptr) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                t0 += sdz[j] * wd[j][0] + gp[j] * wr[j][0];
+                t1 += sdz[j] * wd[j][1] + gp[j] * wr[j][1];
+            }
+            t0 = warp_sum(t0); t1 = warp_sum(t1);
+            if (lane == 0) {
+                a.grad_x_dst[(size_t)v * FD] = t0;
+                if (FD > 1) a.grad_x_dst[(size_t)v * FD + 1] = t1;
+            }
+        }
+    }
+
+    // ---- CTA reduction in a fixed warp order, then one partial row per CTA
+    const int oWs = 0, obs = H * FS, oWd = obs + H, obd = oWd + H * FD, oat = obd + H, oWr = oat + H,
+              obr = oWr + H * FD, P = obr + H;
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int ch = lane * CPL + j;
+                auto put = [&](int idx, float val) { red[idx] = (w == 0) ? val : red[idx] + val; };
+#pragma unroll
+                for (int f = 0; f < FS; ++f) put(oWs + ch * FS + f, g_ws[j][f]);
+                put(obs + ch, g_bsd[j] + g_bsm[j]);
+                put(oWd + ch * FD, g_wd[j][0]);
+                if (FD > 1) put(oWd + ch * FD + 1, g_wd[j][1]);
+                put(obd + ch, g_bsd[j]);
+                put(oat + ch, g_at[j]);
+                put(oWr + ch * FD, g_wr[j][0]);
+                if (FD > 1) put(oWr + ch * FD + 1, g_wr[j][1]);
+                put(obr + ch, g_br[j]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < P; i += 128) a.partial[(size_t)blockIdx.x * P + i] = red[i];
+}
+
+// out[i] = sum_p partial[p*P + i], fixed order: 8 slices of parts per column, combined in slice order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int P,
+                                                              float* __restrict__ out) {
+    __shared__ float sm[8][32];
+    const int col = blockIdx.x * 32 + threadIdx.x % 32, slice = threadIdx.x / 32;
+    float acc = 0.f;
+    if (col < P)
+        for (int p = slice; p < nparts; p += 8) acc += partial[(size_t)p * P + col];
+    sm[slice][threadIdx.x % 32] = acc;
+    __syncthreads();
+    if (slice == 0 && col < P) {
+        float t = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) t += sm[s][threadIdx.x];
+        out[col] = t;
+    }
+}
+
+static int bwd_grid(int64_t n_dst) {
+    int64_t need = (n_dst + 3) / 4;
+    int64_t cap = (int64_t)kNumSMs * 4;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <int FS, int HEADS>
+static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
+    const int H = HEADS * a.D;
+    const bool small = n_edges <= 12 * (int64_t)a.n_dst;           // mean in-degree <= 12: 8 lanes per destination
+    const int gs = small ? 8 : 32;
+    const int gpb = 256 / gs;
+    int64_t need = ((int64_t)a.n_dst + gpb - 1) / gpb;
+    int64_t cap = (int64_t)kNumSMs * 8;
+    const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
+    const size_t smem = (size_t)H * 3 * sizeof(float4) + (size_t)gpb * (2 * H + 2) * sizeof(float);
+    if (small) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gatv2_fwd_kernel<FS, HEADS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gatv2_fwd_kernel<FS, HEADS, 8><<<grid, 256, smem, st>>>(a);
+    } else {
+        gatv2_fwd_kernel<FS, HEADS, 32><<<grid, 256, smem, st>>>(a);
+    }
+    return check_launch("ubs_gatv2_fwd");
+}
+
+template <int FS, int HEADS>
+static int launch_bwd(const GatArgs& a, int H, cudaStream_t st) {
+    const int grid = bwd_grid(a.n_dst);
+    switch (H / 32) {
+        case 1: gatv2_bwd_kernel<FS, 1, HEADS><<<grid, 128, 0, st>>>(a); break;
+        case 2: gatv2_bwd_kernel<FS, 2, HEADS><<<grid, 128, 0, st>>>(a); break;
+        case 4: gatv2_bwd_kernel<FS, 4, HEADS><<<grid, 128, 0, st>>>(a); break;
+        default: set_error("ubs_gatv2_bwd: H=%d unsupported (32, 64, 128)", H); return 2;
+    }
+    return check_launch("ubs_gatv2_bwd");
+}
+
+static int check_shape(const char* fn, int F_s, int F_d, int heads, int D, float slope) {
+    const int H = heads * D;
+    if (F_s < 1 || F_s > 4 || F_d < 1 || F_d > 2) { set_error("%s: fused path needs F_s<=4, F_d<=2 (got %d,%d)", fn, F_s, F_d); return 2; }
+    if (!(heads == 1 || heads == 2 || heads == 4 || heads == 8)) { set_error("%s: heads must be 1,2,4,8 (got %d)", fn, heads); return 2; }
+    if (!(H == 32 || H == 64 || H == 128)) { set_error("%s: heads*D must be 32, 64 or 128 (got %d)", fn, H); return 2; }
+    if (!(slope >= 0.f && slope <= 1.f)) { set_error("%s: negative_slope must be in [0,1] (got %g)", fn, slope); return 2; }
+    return 0;
+}
+
+}  // namespace ubs
+
+#define UBS_DISPATCH_FS_HEADS(FN, ...)                                                      \
+    switch (F_s * 16 + heads) {                                                             \
+        case 1 * 16 + 1: rc = FN<1, 1>(__VA_ARGS__); break;                                 \
+        case 1 * 16 + 2: rc = FN<1, 2>(__VA_ARGS__); break;                                 \
+        case 1 * 16 + 4: rc = FN<1, 4>(__VA_ARGS__); break;                                 \
+        case 1 * 16 + 8: rc = FN<1, 8>(__VA_ARGS__); break;                                 \
+        case 2 * 16 + 1: rc = FN<2, 1>(__VA_ARGS__); break;                                 \
+        case 2 * 16 + 2: rc = FN<2, 2>(__VA_ARGS__); break;                                 \
+        case 2 * 16 + 4: rc = FN<2, 4>(__VA_ARGS__); break;                                 \
+        case 2 * 16 + 8: rc = FN<2, 8>(__VA_ARGS__); break;                                 \
+        case 3 * 16 + 1: rc = FN<3, 1>(__VA_ARGS__); break;                                 \
+        case 3 * 16 + 2: rc = FN<3, 2>(__VA_ARGS__); break;                                 \
+        case 3 * 16 + 4: rc = FN<3, 4>(__VA_ARGS__); break;                                 \
+        case 3 * 16 + 8: rc = FN<3, 8>(__VA_ARGS__); break;                                 \
+        case 4 * 16 + 1: rc = FN<4, 1>(__VA_ARGS__); break;                                 \
+        case 4 * 16 + 2: rc = FN<4, 2>(__VA_ARGS__); break;                                 \
+        case 4 * 16 + 4: rc = FN<4, 4>(__VA_ARGS__); break;                                 \
+        case 4 * 16 + 8: rc = FN<4, 8>(__VA_ARGS__); break;                                 \
+        default: ubs::set_error("unsupported (F_s, heads)"); rc = 2;                        \
+    }
+
+extern "C" UBS_API int ubs_gatv2_fwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                             const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                             const float* attn, const float* W_res, const float* b_res,
+                             float* out, float* smax, float* ssum, int64_t n_dst, int64_t n_edges,
+                             int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream) {
+    if (int rc = ubs::check_shape("ubs_gatv2_fwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(n_dst >= 0 && n_dst < (1ll << 31) && n_edges >= 0 && n_edges < (1ll << 31), "ubs_gatv2_fwd: sizes out of range");
+    UBS_REQUIRE((smax == nullptr) == (ssum == nullptr), "ubs_gatv2_fwd: smax and ssum must both be given or both NULL");
+    UBS_REQUIRE(!(flags & UBS_GAT_RESIDUAL) || W_res != nullptr, "ubs_gatv2_fwd: residual flag without W_res");
+    UBS_REQUIRE(((uintptr_t)x_src % (F_s == 4 ? 16 : F_s == 2 ? 8 : 4)) == 0, "ubs_gatv2_fwd: x_src misaligned");
+    if (n_dst == 0) return 0;
+    ubs::GatArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.indptr = indptr; a.src_idx = src_idx;
+    a.W_src = W_src; a.b_src = b_src; a.W_dst = W_dst; a.b_dst = b_dst; a.attn = attn; a.W_res = W_res; a.b_res = b_res;
+    a.out = out; a.smax = smax; a.ssum = ssum;
+    a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
+    int rc = 0;
+    UBS_DISPATCH_FS_HEADS(ubs::launch_fwd, a, n_edges, (cudaStream_t)stream)
+    return rc;
+}
+
+extern "C" UBS_API int64_t ubs_gatv2_bwd_workspace(int64_t n_dst, int F_s, int F_d, int heads, int D) {
+    return (int64_t)ubs::bwd_grid(n_dst) * ubs::gat_param_count(heads * D, F_s, F_d);
+}
+
+extern "C" UBS_API int ubs_gatv2_bwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                             const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                             const float* attn, const float* W_res, const float* b_res,
+                             const float* out, const float* grad_out, const float* smax, const float* ssum,
+                             float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                             int64_t n_dst, int64_t n_edges, int64_t n_src, int F_s, int F_d, int heads, int D,
+                             float negative_slope, int flags, void* stream) {
+    (void)n_src;
+    if (int rc = ubs::check_shape("ubs_gatv2_bwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(n_dst >= 0 && n_dst < (1ll << 31) && n_edges >= 0 && n_edges < (1ll << 31), "ubs_gatv2_bwd: sizes out of range");
+    UBS_REQUIRE(smax && ssum && out && grad_out && grad_params && workspace, "ubs_gatv2_bwd: NULL argument");
+    UBS_REQUIRE(((uintptr_t)x_src % (F_s == 4 ? 16 : F_s == 2 ? 8 : 4)) == 0, "ubs_gatv2_bwd: x_src misaligned");
+    const int H = heads * D;
+    UBS_REQUIRE(32 % heads == 0 && (H / heads) % (H / 32) == 0, "ubs_gatv2_bwd: head layout unsupported");
+    const int P = ubs::gat_param_count(H, F_s, F_d);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_dst == 0) {
+        cudaMemsetAsync(grad_params, 0, sizeof(float) * P, st);
+        return 0;
+    }
+    ubs::GatArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.indptr = indptr; a.src_idx = src_idx;
+    a.W_src = W_src; a.b_src = b_src; a.W_dst = W_dst; a.b_dst = b_dst; a.attn = attn; a.W_res = W_res; a.b_res = b_res;
+    a.grad_out = grad_out; a.out_in = out; a.smax_in = smax; a.ssum_in = ssum;
+    a.partial = workspace; a.grad_x_src = grad_x_src; a.grad_x_dst = grad_x_dst;
+    a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
+    int rc = 0;
+    UBS_DISPATCH_FS_HEADS(ubs::launch_bwd, a, H, st)
+    if (rc) return rc;
+    ubs::reduce_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(workspace, ubs::bwd_grid(n_dst), P, grad_params);
+    return ubs::check_launch("ubs_gatv2_bwd(reduce)");
+}

@@ -45,11 +45,14 @@ class RelCSR:
                 already destination-sorted (slot j == edge j).
     """
 
-    __slots__ = ("indptr", "src_idx", "eid", "n_src", "n_dst", "n_edges")
+    __slots__ = ("indptr", "src_idx", "eid", "n_src", "n_dst", "n_edges", "block", "mask")
 
-    def __init__(self, indptr, src_idx, eid, n_src, n_dst, n_edges):
+    def __init__(self, indptr, src_idx, eid, n_src, n_dst, n_edges, block=None, mask=None):
         self.indptr, self.src_idx, self.eid = indptr, src_idx, eid
         self.n_src, self.n_dst, self.n_edges = int(n_src), int(n_dst), int(n_edges)
+        # block-diagonal form (comm graphs): nodes come in consecutive blocks of `block` and bit i of mask[v]
+        # says whether the i-th node of v's block sends to v.  Filled by RelGraph.block_mask().
+        self.block, self.mask = block, mask
 
     @property
     def is_star(self) -> bool:
@@ -57,11 +60,13 @@ class RelCSR:
 
     def to(self, device, non_blocking=False) -> "RelCSR":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
-        return RelCSR(mv(self.indptr), mv(self.src_idx), mv(self.eid), self.n_src, self.n_dst, self.n_edges)
+        return RelCSR(mv(self.indptr), mv(self.src_idx), mv(self.eid), self.n_src, self.n_dst, self.n_edges,
+                      self.block, mv(self.mask))
 
     def pin_memory(self) -> "RelCSR":
         mv = lambda t: None if t is None else t.pin_memory()
-        return RelCSR(mv(self.indptr), mv(self.src_idx), mv(self.eid), self.n_src, self.n_dst, self.n_edges)
+        return RelCSR(mv(self.indptr), mv(self.src_idx), mv(self.eid), self.n_src, self.n_dst, self.n_edges,
+                      self.block, mv(self.mask))
 
     def dst_of_slot(self) -> th.Tensor:
         """int64 destination id of every CSR slot (expands indptr)."""
@@ -178,7 +183,7 @@ class HeteroGraph:
         self._eframes: Dict[tuple, dict] = eframes if eframes is not None else {c: {} for c in self._cets}
         self._bnn: Dict[str, List[int]] = bnn if bnn is not None else {t: [self._nn[t]] for t in self._ntypes}
         self._bne: Dict[tuple, List[int]] = bne if bne is not None else {
-            c: [int(self._dst[c].numel())] for c in self._cets}
+            c: [self._ne(c)] for c in self._cets}
         self._csr: Dict[tuple, RelCSR] = csr if csr is not None else {}
 
     # ------------------------------------------------------------------ structure
@@ -218,19 +223,39 @@ class HeteroGraph:
 
     def num_edges(self, etype=None) -> int:
         if etype is None:
-            return sum(int(d.numel()) for d in self._dst.values())
-        return int(self._dst[self.to_canonical_etype(etype)].numel())
+            return sum(self._ne(c) for c in self._cets)
+        return self._ne(self.to_canonical_etype(etype))
 
     number_of_edges = num_edges
 
     def edges(self, etype=None):
         c = self._only_etype() if etype is None else self.to_canonical_etype(etype)
+        return self._edge_list(c)
+
+    def _ne(self, c) -> int:
+        d = self._dst.get(c)
+        return int(d.numel()) if d is not None else self._csr[c].n_edges
+
+    def _edge_list(self, c):
+        """(src, dst) int64 in edge-id order; rebuilt from the CSR (and its slot -> edge-id map) when the graph
+        was moved across devices or built CSR-first (edge lists are not shipped to the GPU)."""
+        if self._dst.get(c) is None:
+            r = self._csr[c]
+            u, v = r.src_of_slot(), r.dst_of_slot()
+            if r.eid is not None:
+                uu, vv = th.empty_like(u), th.empty_like(v)
+                uu[r.eid], vv[r.eid] = u, v
+                u, v = uu, vv
+            self._src[c], self._dst[c] = u, v
         return self._src[c], self._dst[c]
 
     @property
     def device(self):
+        for r in self._csr.values():
+            return r.indptr.device
         for d in self._dst.values():
-            return d.device
+            if d is not None:
+                return d.device
         return th.device("cpu")
 
     @property
@@ -253,7 +278,7 @@ class HeteroGraph:
         c = self._only_etype() if etype is None else self.to_canonical_etype(etype)
         r = self._csr.get(c)
         if r is None:
-            r = RelCSR.from_edges(self._src[c], self._dst[c], self._nn[c[0]], self._nn[c[2]])
+            r = RelCSR.from_edges(self._src[c], self._dst[c], self._nn[c[0]], self._nn[c[2]])  # lists exist here
             self._csr[c] = r
         return r
 
@@ -309,9 +334,11 @@ class HeteroGraph:
         if build_csr:
             for c in self._cets:
                 self.csr(c)
+                if c[0] == c[2]:
+                    RelGraph(self, c).block_mask()
         return HeteroGraph(
             self._ntypes, self._cets, self._nn,
-            {c: fn_t(t) for c, t in self._src.items()}, {c: fn_t(t) for c, t in self._dst.items()},
+            {c: None for c in self._cets}, {c: None for c in self._cets},     # edge lists stay behind (lazy)
             {t: {k: fn_t(v) for k, v in f.items()} for t, f in self._nframes.items()},
             {c: {k: fn_t(v) for k, v in f.items()} for c, f in self._eframes.items()},
             {t: list(v) for t, v in self._bnn.items()}, {c: list(v) for c, v in self._bne.items()},
@@ -334,7 +361,7 @@ class HeteroGraph:
 
     def __repr__(self):
         nn_ = {t: self._nn[t] for t in self._ntypes}
-        ne = {c: int(self._dst[c].numel()) for c in self._cets}
+        ne = {c: self._ne(c) for c in self._cets}
         return f"HeteroGraph(num_nodes={nn_}, num_edges={ne}, batch_size={self.batch_size})"
 
 
@@ -363,7 +390,7 @@ class RelGraph:
         return self._g.csr(self._c)
 
     def edges(self):
-        return self._g._src[self._c], self._g._dst[self._c]
+        return self._g._edge_list(self._c)
 
     def num_src_nodes(self):
         return self._g._nn[self._c[0]]
@@ -380,12 +407,31 @@ class RelGraph:
     number_of_nodes = num_nodes
 
     def num_edges(self):
-        return int(self._g._dst[self._c].numel())
+        return self._g._ne(self._c)
 
     number_of_edges = num_edges
 
     def uniform_block(self) -> Optional[int]:
         return self._g.uniform_block(self._c[2])
+
+    def block_mask(self):
+        """``(block, mask)`` of a block-diagonal homogeneous relation, or ``None`` when the relation is not a
+        batch of equally sized graphs with at most 32 nodes each.  ``mask`` is int32 (uint32 bit pattern)."""
+        st, _, dt = self._c
+        if st != dt:
+            return None
+        c = self.csr()
+        if c.mask is None:
+            U = self.uniform_block()
+            if U is None or U < 1 or U > 32:
+                return None
+            dst, src = c.dst_of_slot(), c.src_of_slot()
+            local = src - (dst // U) * U
+            bits = th.zeros(c.n_dst, dtype=th.int64, device=dst.device)
+            if c.n_edges:
+                bits.index_add_(0, dst, th.ones_like(local) << local)   # edges are unique => add == or
+            c.block, c.mask = U, bits.to(th.int32)
+        return c.block, c.mask
 
     def in_degrees(self):
         ip = self.csr().indptr
@@ -497,8 +543,11 @@ def batch(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
     src, dst, bne, csr = {}, {}, {}, {}
     for c in g0._cets:
         st, _, dt = c
-        src[c] = th.cat([g._src[c] + noff[st][i] for i, g in enumerate(graphs)])
-        dst[c] = th.cat([g._dst[c] + noff[dt][i] for i, g in enumerate(graphs)])
+        if all(g._dst.get(c) is not None for g in graphs):
+            src[c] = th.cat([g._src[c] + noff[st][i] for i, g in enumerate(graphs)])
+            dst[c] = th.cat([g._dst[c] + noff[dt][i] for i, g in enumerate(graphs)])
+        else:
+            src[c] = dst[c] = None                      # rebuilt lazily from the composed CSR
         bne[c] = [x for g in graphs for x in g._bne[c]]
         parts = [g.csr(c) for g in graphs]
         eoff, acc = [], 0
@@ -523,7 +572,7 @@ def batch(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
         csr[c] = RelCSR(indptr, src_idx, eid, nn_[st], nn_[dt], acc)
     nframes = {t: _cat_frames([g._nframes[t] for g in graphs], [g._nn[t] for g in graphs], f"node[{t}]")
                for t in g0._ntypes}
-    eframes = {c: _cat_frames([g._eframes[c] for g in graphs], [int(g._dst[c].numel()) for g in graphs],
+    eframes = {c: _cat_frames([g._eframes[c] for g in graphs], [g._ne(c) for g in graphs],
                               f"edge[{c}]") for c in g0._cets}
     return HeteroGraph(g0._ntypes, g0._cets, nn_, src, dst, nframes, eframes, bnn, bne, csr)
 
@@ -540,9 +589,9 @@ def merge(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
     nn_ = {t: max(g._nn[t] for g in graphs) for t in g0._ntypes}
     src, dst, csr = {}, {}, {}
     for c in g0._cets:
-        src[c] = th.cat([g._src[c] for g in graphs])
-        dst[c] = th.cat([g._dst[c] for g in graphs])
-        holders = [g for g in graphs if g._dst[c].numel() > 0]
+        src[c] = th.cat([g._edge_list(c)[0] for g in graphs])
+        dst[c] = th.cat([g._edge_list(c)[1] for g in graphs])
+        holders = [g for g in graphs if g._ne(c) > 0]
         if len(holders) == 1:  # CSR can be reused; only the destination count may grow
             p = holders[0].csr(c)
             indptr = p.indptr
@@ -562,6 +611,6 @@ def merge(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
     for c in g0._cets:
         keys = [k for g in graphs for k in g._eframes[c]]
         for k in dict.fromkeys(keys):
-            if all(k in g._eframes[c] or g._dst[c].numel() == 0 for g in graphs):
+            if all(k in g._eframes[c] or g._ne(c) == 0 for g in graphs):
                 eframes[c][k] = th.cat([g._eframes[c][k] for g in graphs if k in g._eframes[c]])
     return HeteroGraph(g0._ntypes, g0._cets, nn_, src, dst, nframes, eframes, None, None, csr)

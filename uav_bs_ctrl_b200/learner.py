@@ -1,0 +1,256 @@
+"""Learner mirrors: the callers of the hot path (reference ``algos/madrqn/learner.py:14-201``, ``algos/drqn/learner.py``).
+
+Same constructor / ``init_hidden`` / ``act`` / ``cache`` / ``update`` / checkpoint surface as the reference's
+``MultiAgentQLearner``, with three additions the north-star needs:
+
+* **vector envs** — one graph carries ``n_envs`` env instances (``N = n_envs * n_agents`` agent rows); ε-greedy draws
+  one uniform per env (the reference draws one per call for its single env, ``learner.py:75-78``);
+* **device-resident replay** — ``cache`` keeps whatever graph it is handed (the device copy ``act`` staged), so
+  ``update`` never re-uploads observations (reference: ``obs[t].to(device)`` at ``learner.py:116``);
+* **data parallel** — a flat-bucket NCCL all-reduce of the policy gradients between ``loss.backward()`` and
+  ``clip_grad_value_`` (``learner.py:158-159``), see ``dist.py``.
+
+Loss math (``learner.py:118-154``), value clipping, AdamW, polyak target and checkpoint dict keys are the reference's.
+"""
+from __future__ import annotations
+
+import random
+from collections import deque
+from copy import deepcopy
+from typing import List
+
+import torch as th
+import torch.nn as nn
+from torch.optim import AdamW
+
+from . import dist
+from .agents import REGISTRY as agent_REGISTRY, DRQN_REGISTRY
+from .graph import HeteroGraph, batch as graph_batch
+
+SCHEME = ("obs", "h", "state", "act", "rew", "done")
+
+
+def cat(data_list):
+    """Reference ``algos/common.py:40-47``: ``th.cat`` for tensors, graph batching for graphs."""
+    if isinstance(data_list[0], th.Tensor):
+        return th.cat(data_list)
+    if isinstance(data_list[0], HeteroGraph):
+        return graph_batch(data_list)
+    raise TypeError("Unrecognised observation type.")
+
+
+class ReplayBuffer:
+    """Replay of fixed-length sequences (reference ``algos/madrqn/buffer.py:7-42``).  Entries may live on the GPU."""
+
+    def __init__(self, capacity, max_seq_len, scheme=SCHEME):
+        self.memory = deque(maxlen=capacity)
+        self.max_seq_len, self.scheme = max_seq_len, scheme
+        self.curr_seq = {k: [] for k in scheme}
+        self.ptr = 0
+
+    def push(self, transition: dict):
+        for k, v in transition.items():
+            if k in self.scheme:
+                self.curr_seq[k].append(v)
+        self.ptr += 1
+        if self.ptr == self.max_seq_len:
+            for k in ("obs", "h", "state"):
+                if k in self.scheme:
+                    self.curr_seq[k].append(transition.get("next_" + k))
+            self.memory.append(self.curr_seq)
+            self.curr_seq = {k: [] for k in self.scheme}
+            self.ptr = 0
+
+    def sample(self, batch_size: int):
+        return random.sample(self.memory, batch_size)
+
+    def __len__(self):
+        return len(self.memory)
+
+
+class MultiAgentQLearner:
+    """Multi-agent recurrent Q-learner (reference ``algos/madrqn/learner.py:14-201``, no-mixer path)."""
+
+    def __init__(self, env_info, args):
+        self.args = args
+        self.device = th.device(args.device)
+        self.obs_shape, self.state_shape = env_info["obs_shape"], env_info.get("state_shape")
+        self.n_actions, self.n_agents = env_info["n_actions"], env_info["n_agents"]
+        self.n_envs = int(getattr(args, "n_envs", 1))
+
+        self.policy_net = self._build_agent().to(self.device)
+        self.target_net = self._build_agent().to(self.device)
+        dist.sync_params(self.policy_net)
+        self.target_net.load_state_dict(self.policy_net.state_dict())
+        self.target_net.eval()
+        self.params = list(self.policy_net.parameters())
+        if getattr(args, "mixer", False):
+            raise NotImplementedError("QMixer is outside the hot-path scope (SURVEY §2 row 3)")
+        self.mixer = None
+
+        self.max_seq_len = args.max_seq_len if args.max_seq_len is not None else env_info["episode_limit"]
+        self.gamma, self.polyak, self.batch_size = args.gamma, args.polyak, args.batch_size
+        self.buffer = ReplayBuffer(args.replay_size, self.max_seq_len)
+        self.loss_fn = nn.MSELoss()
+        self.optimizer = AdamW(self.params, lr=args.lr)
+        self.grad_bucket = dist.FlatGradBucket(self.params)
+        self.anneal_lr = getattr(args, "anneal_lr", False)
+        if self.anneal_lr:
+            self.lr_scheduler = th.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=lambda e: max(0.4, 1 - e / 100))
+        self.double_q = args.double_q
+
+    # ------------------------------------------------------------------------------------------ acting
+    def init_hidden(self, batch_size=1):
+        return self.policy_net.init_hidden().expand(self.n_agents * batch_size, -1)
+
+    def _build_agent(self):
+        if (self.args.o == "mlp") and (self.args.c is None):
+            return agent_REGISTRY["rnn"](self.obs_shape, self.n_actions, self.args)
+        return agent_REGISTRY["gnn"](self.obs_shape, self.n_actions, self.args)
+
+    def stage(self, obs):
+        """Host → device copy of an observation (asynchronous when the host graph is pinned)."""
+        return obs.to(self.device, non_blocking=True)
+
+    def act(self, obs, h, eps_thres):
+        """ε-greedy action selection (reference ``learner.py:69-80``).  Single env: returns ``(list, h)`` exactly
+        like the reference.  Vector envs: returns a device tensor of ``n_envs * n_agents`` actions."""
+        obs, h = obs.to(self.device, non_blocking=True), h.to(self.device)
+        with th.no_grad():
+            logits, h = self.policy_net(obs, h)
+        if self.n_envs == 1:
+            if random.random() > eps_thres:
+                acts = th.argmax(logits, 1)
+            else:
+                acts = th.randint(self.n_actions, size=(self.n_agents,), dtype=th.long)
+            return acts.tolist(), h
+        greedy = th.argmax(logits, 1)
+        explore = (th.rand(self.n_envs, device=self.device) <= eps_thres).repeat_interleave(self.n_agents)
+        rnd = th.randint(self.n_actions, size=greedy.shape, device=self.device)
+        return th.where(explore, rnd, greedy), h
+
+    def cache(self, obs, h, state, act, rew, next_obs, next_h, next_state, done, bad_mask):
+        """Reference ``learner.py:82-92``.  ``done`` / ``bad_mask`` are scalars (single env) or ``(n_envs,)`` tensors."""
+        as_t = lambda x, dt: x.to(dt) if isinstance(x, th.Tensor) else th.tensor(x, dtype=dt)
+        rew = as_t(rew, th.float32)
+        if self.args.share_reward:
+            rew = rew.reshape(self.n_envs, -1).mean(1, keepdim=True)
+        done_t = as_t(done, th.float32).reshape(self.n_envs, 1)
+        bad_t = as_t(bad_mask if bad_mask is not None else 0, th.float32).reshape(-1, 1)
+        keep = (1 - done_t).repeat_interleave(self.n_agents, 0).to(next_h.device)
+        transition = dict(obs=obs, h=h, state=state, act=as_t(act, th.long).reshape(-1, 1),
+                          rew=rew.reshape(self.n_envs, -1), next_obs=next_obs, next_h=keep * next_h,
+                          next_state=next_state, done=(1 - bad_t) * done_t)
+        self.buffer.push(transition)
+
+    # ------------------------------------------------------------------------------------------ learning
+    def _unroll(self, obs: List[HeteroGraph], h, h_targ):
+        """Reference ``learner.py:118-129``: T policy steps with grad + T target steps without + one more policy step."""
+        agent_out, target_out = [], []
+        T = self.max_seq_len
+        for t in range(T):
+            logits, h = self.policy_net(obs[t], h)
+            agent_out.append(logits)
+            with th.no_grad():
+                next_logits, h_targ = self.target_net(obs[t + 1], h_targ)
+                target_out.append(next_logits)
+        logits, h = self.policy_net(obs[T], h)
+        agent_out.append(logits)
+        return th.stack(agent_out), th.stack(target_out)
+
+    def compute_loss(self, obs, h, h_targ, acts, rews, dones):
+        T = self.max_seq_len
+        agent_out, target_out = self._unroll(obs, h, h_targ)
+        qvals = agent_out[:-1].gather(2, acts)
+        if not self.double_q:
+            next_vals = target_out.max(2, keepdim=True)[0]
+        else:
+            next_acts = th.argmax(agent_out[1:].detach(), 2, keepdim=True)
+            next_vals = target_out.gather(2, next_acts)
+        n_seq = rews.shape[1]
+        qvals = qvals.view(T, n_seq, self.n_agents)
+        next_vals = next_vals.view(T, n_seq, self.n_agents)
+        rews, dones = rews.expand_as(next_vals), dones.expand_as(next_vals)
+        target_qvals = rews + self.gamma * (1 - dones) * next_vals
+        return self.loss_fn(qvals, target_qvals), qvals
+
+    def gather_batch(self, samples):
+        """Reference ``learner.py:99-116``: per-timestep ``cat`` over the sampled sequences, then move to device."""
+        T = self.max_seq_len
+        batch = {k: [] for k in self.buffer.scheme}
+        keys = [k for k in batch if samples[0][k] and samples[0][k][0] is not None]
+        for t in range(T):
+            for k in keys:
+                batch[k].append(cat([s[k][t] for s in samples]))
+        for k in ("obs", "h", "state"):
+            if k in keys:
+                batch[k].append(cat([s[k][T] for s in samples]))
+        dev = self.device
+        acts = th.stack(batch["act"]).to(dev)
+        rews = th.stack(batch["rew"]).to(dev)
+        dones = th.stack(batch["done"]).to(dev)
+        h, h_targ = batch["h"][0].to(dev), batch["h"][1].to(dev)
+        obs = [o.to(dev) for o in batch["obs"]]
+        return obs, h, h_targ, acts, rews, dones
+
+    def update(self, samples=None, sync=True):
+        """One BPTT update (reference ``learner.py:94-173``).  ``samples`` overrides the random replay draw."""
+        if samples is None:
+            assert len(self.buffer) >= self.batch_size, "Insufficient samples for update."
+            samples = self.buffer.sample(self.batch_size)
+        obs, h, h_targ, acts, rews, dones = self.gather_batch(samples)
+        loss, qvals = self.compute_loss(obs, h, h_targ, acts, rews, dones)
+
+        self.grad_bucket.zero_()
+        loss.backward()
+        self.grad_bucket.rebind()
+        dist.avg_grads(self.grad_bucket)                                     # DP: one flat all-reduce
+        nn.utils.clip_grad_value_(self.policy_net.parameters(), clip_value=1)
+        self.optimizer.step()
+        with th.no_grad():
+            pp, tp = list(self.policy_net.parameters()), list(self.target_net.parameters())
+            th._foreach_mul_(tp, self.polyak)
+            th._foreach_add_(tp, pp, alpha=1 - self.polyak)
+        if sync:
+            return dict(LossQ=loss.item(), QVals=qvals.detach().cpu().numpy())
+        return dict(LossQ=loss.detach(), QVals=qvals.detach())
+
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, path, stamp):
+        checkpoint = dict(stamp)
+        checkpoint["model_state_dict"] = self.policy_net.state_dict()
+        checkpoint["optimizer_state_dict"] = self.optimizer.state_dict()
+        if self.anneal_lr:
+            checkpoint["lr_scheduler_state_dict"] = self.lr_scheduler.state_dict()
+        th.save(checkpoint, path)
+
+    def load_checkpoint(self, path):
+        checkpoint = th.load(path, map_location=self.device)
+        stamp = dict(epoch=checkpoint["epoch"], t=checkpoint["t"])
+        self.policy_net.load_state_dict(checkpoint["model_state_dict"])
+        self.target_net.load_state_dict(self.policy_net.state_dict())
+        self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        if self.anneal_lr:
+            self.lr_scheduler.load_state_dict(checkpoint["lr_scheduler_state_dict"])
+        return stamp
+
+
+class QLearner(MultiAgentQLearner):
+    """Single-agent DRQN learner (reference ``algos/drqn/learner.py:15-150``): one agent, ``max`` target, no double-Q."""
+
+    def __init__(self, env_info, args):
+        info = dict(env_info)
+        info.setdefault("n_agents", 1)
+        info.setdefault("state_shape", None)
+        for k, v in dict(o="gnn", c=None, share_reward=False, double_q=False, dueling=False, mixer=False).items():
+            if not hasattr(args, k):
+                setattr(args, k, v)
+        super().__init__(info, args)
+
+    def _build_agent(self):
+        kind = "rnn" if isinstance(self.obs_shape, int) else "gnn"
+        return DRQN_REGISTRY[kind](self.obs_shape, self.n_actions, self.args)
+
+    def act(self, obs, h, eps_thres):
+        acts, h = super().act(obs, h, eps_thres)
+        return (acts[0] if isinstance(acts, list) else acts), h

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the MADRQN exp3 hot path (BASELINE.json metric).
+
+One *step* of this bench = one training cycle of the reference's loop cadence (``algos/madrqn/run.py:81-99``) on
+B parallel env instances per GPU: T vector-steps of ``learner.act`` (graph encoder + TarMAC + GRU + Q head +
+ε-greedy) on replayed synthetic observations, the T ``learner.cache`` calls, and one ``learner.update`` (BPTT over
+the B sequences × T just collected: T+1 policy forwards, T target forwards, double-Q loss, backward, gradient
+all-reduce, value clip, AdamW, polyak).  env-steps per step = B·T per GPU (one env-step = one transition of one
+env instance, all U agents acting).  Workload = BASELINE configs[1]: exp3, 8 UBS × 80 GT, hidden 64, 256 envs per
+GPU, every GT visible (full degree: E_seen = N·G, the heaviest degree profile), T = episode_limit = 50.
+
+    python bench.py --gpus N --steps K --warmup W                  # this framework
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle (DGL-equivalent restatement)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §d for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch as th  # noqa: E402
+
+METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
+U, G, H, HEADS, M, K, N_ACT = 8, 80, 64, 4, 64, 16, 9
+OBS_SHAPE = {"agent": 2, "ubs": 2, "gt": 4}
+
+
+def model_args(device, T, n_envs):
+    """exp3 model / optimiser settings: ``algos/madrqn/config.py`` defaults + ``run_exp3.py:30-54`` overrides, with
+    hidden_size=64 as BASELINE.json names it."""
+    return SimpleNamespace(device=str(device), o="gnn", c="tarmac", share_reward=False, hidden_size=H, n_layers=2,
+                           n_heads=HEADS, msg_size=M, key_size=K, n_rounds=1, lr=2.5e-4, gamma=0.99, polyak=0.999,
+                           batch_size=1, replay_size=2, max_seq_len=T, anneal_lr=False, double_q=True, dueling=False,
+                           mixer=False, n_envs=n_envs)
+
+
+def make_episode(B, T, profile, seed):
+    """T+1 host-resident batched observation graphs + rewards / dones, seeded (SURVEY §8(d) distributions)."""
+    from uav_bs_ctrl_b200.builder import build_obs_graph_batch
+    from uav_bs_ctrl_b200.synth import synth_dense_obs
+    graphs = [build_obs_graph_batch(*synth_dense_obs(B, U, G, profile, seed=seed + t)) for t in range(T + 1)]
+    gen = th.Generator().manual_seed(seed + 7919)
+    rews = th.rand(T, B, U, generator=gen)
+    dones = th.zeros(T, B)
+    dones[T - 1] = 1.0                              # episode_limit reached on the last step (bad_mask mutes it)
+    bad = dones.clone()
+    return graphs, rews, dones, bad
+
+
+def graph_bytes(g):
+    n = 0
+    for f in g._nframes.values():
+        for v in f.values():
+            n += v.numel() * v.element_size()
+    for r in g._csr.values():
+        for t in (r.indptr, r.src_idx, r.eid, r.mask):
+            if t is not None:
+                n += t.numel() * t.element_size()
+    return n
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def train_cycle(learner, obs, rews, dones, bad, T, B, eps, host_io, acts_host=None):
+    """One step of the bench.  ``host_io``: observations come from pinned host memory and actions / loss go back."""
+    dev = learner.device
+    h = learner.init_hidden(B).to(dev)
+    o = learner.stage(obs[0]) if host_io else obs[0]
+    for t in range(T):
+        acts, h2 = learner.act(o, h, eps)
+        if host_io:                                     # the env needs the actions on the host before it can step
+            acts_host[t].copy_(acts, non_blocking=True)
+            th.cuda.current_stream().synchronize()
+        o2 = learner.stage(obs[t + 1]) if host_io else obs[t + 1]
+        learner.cache(o, h, None, acts, rews[t], o2, h2, None, dones[t], bad[t])
+        o, h = o2, h2
+    return learner.update(samples=[learner.buffer.memory[-1]], sync=host_io)
+
+
+def algorithmic_bytes_gat(meta):
+    """star-layout GATv2 relation.  fwd 4(E·F_s + N·F_d + N+1 + N·H) + 4P (+8·N·heads when stats are
+    saved); bwd 4(E·F_s + N·F_d + N+1 + 2N·H + 2N·heads) + 8P."""
+    n, e, fs, fd, heads, d, train = meta
+    Hh = heads * d
+    P = Hh * (fs + 1) + 2 * Hh * (fd + 1) + Hh
+    fwd = 4 * (e * fs + n * fd + (n + 1) + n * Hh) + 4 * P + (8 * n * heads if train else 0)
+    bwd = 4 * (e * fs + n * fd + (n + 1) + 2 * n * Hh + 2 * n * heads) + 8 * P
+    return fwd, bwd
+
+
+def run_ours(a):
+    from uav_bs_ctrl_b200 import _lib, dist, ops
+    from uav_bs_ctrl_b200.learner import MultiAgentQLearner
+    local = dist.init_from_env("nccl")
+    world, rank = dist.world_size(), dist.rank()
+    assert th.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    dev = th.device("cuda", local)
+    th.cuda.set_device(dev)
+    _lib.load()
+    B, T = a.envs, a.T
+    th.manual_seed(0)
+    learner = MultiAgentQLearner(dict(obs_shape=OBS_SHAPE, state_shape=None, n_actions=N_ACT, n_agents=U,
+                                      episode_limit=T), model_args(dev, T, B))
+    graphs, rews, dones, bad = make_episode(B, T, a.profile, seed=1234 + 100 * rank)
+    h2d = sum(graph_bytes(g) for g in graphs) + rews.numel() * 4 + dones.numel() * 8
+    d2h = T * B * U * 8 + 4 + T * B * U * 4
+    dev_graphs = [g.to(dev) for g in graphs]
+    dev_rews, dev_dones, dev_bad = rews.to(dev), dones.to(dev), bad.to(dev)
+    eps = 0.05
+
+    def barrier():
+        if world > 1:
+            th.distributed.barrier()
+        th.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        _lib.reset_launch_count()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        launches = _lib.launch_count()
+        clocks = sampler.stop() if sampler else None
+        ms = dist.all_reduce_max_scalar(e0.elapsed_time(e1), dev)
+        return ms, launches, clocks
+
+    # ---- value: inputs resident in HBM
+    ms, launches, clocks = timed(lambda: train_cycle(learner, dev_graphs, dev_rews, dev_dones, dev_bad, T, B, eps, False),
+                                 a.steps, a.warmup, sample_clocks=True)
+    value = world * B * T * a.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host observations in, actions / loss / q-values out, every step
+    e2e = None
+    if not a.no_e2e:
+        pin_graphs = [g.pin_memory() for g in graphs]
+        pin_rews, pin_dones, pin_bad = rews.pin_memory(), dones.pin_memory(), bad.pin_memory()
+        acts_host = th.empty(T, B * U, dtype=th.int64).pin_memory()
+        ms_e, _, _ = timed(lambda: train_cycle(learner, pin_graphs, pin_rews, pin_dones, pin_bad, T, B, eps, True,
+                                               acts_host), a.steps, max(1, a.warmup // 2 + 1))
+        e2e = {"value": world * B * T * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps}
+
+    # ---- roofline of the dominant kernel: CUDA events around every C-ABI call during one extra step
+    roofline = None
+    if rank == 0:
+        ops.TIMER = ops.KernelTimer()
+        train_cycle(learner, dev_graphs, dev_rews, dev_dones, dev_bad, T, B, eps, False)
+        summ = ops.TIMER.summary()
+        ops.TIMER = None
+        dom = max(summ, key=lambda k: summ[k]["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
+            (6650.0, "fallback (B200_PROFILING.md)")
+        if dom.startswith("gatv2"):
+            tot = sum(algorithmic_bytes_gat(m)[0 if dom.endswith("fwd") else 1] for m in summ[dom]["metas"])
+        else:
+            tot = 0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except (OSError, ValueError):
+            pass
+        achieved = tot / (summ[dom]["ms"] * 1e-3) / 1e9 if summ[dom]["ms"] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "launches_timed": summ[dom]["count"], "avg_launch_us": 1e3 * summ[dom]["ms"] / summ[dom]["count"],
+                    "algorithmic_bytes_per_launch": tot / max(1, summ[dom]["count"]),
+                    "timing": "CUDA events around each C-ABI call of one extra step after the timed region",
+                    "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in summ.items()},
+                    "kernel_calls_per_step": {k: v["count"] for k, v in summ.items()}}
+
+    # ---- CPU baseline (oracle, rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu = cpu_reference(B, min(a.cpu_T, T), a.profile, steps=3, warmup=1)
+
+    if world > 1:
+        th.distributed.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, "
+                                       f"{B} envs/GPU, T={T}, degree profile '{a.profile}'",
+                           "env_steps_per_step": world * B * T, "update_batch": f"{B} sequences x {T} per GPU",
+                           "parallelism": f"dp{world}", "l2_policy": "inputs exceed L2: "
+                           f"{h2d / 2**20:.0f} MiB of observations are streamed per step (> 126 MB L2)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": int(launches)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        th.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(B, T, profile, steps, warmup, seed=1234):
+    """Times the CPU oracle (pure-PyTorch restatement of the DGL path — DGL 0.9.0 itself is not installable) on the
+    same cycle with all host threads.  Returns the ``cpu_baseline`` object."""
+    from oracle import gnn_oracle as O
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    args = model_args("cpu", T, B)
+    th.manual_seed(0)
+    policy, target = O.GnnAgent(OBS_SHAPE, N_ACT, args), O.GnnAgent(OBS_SHAPE, N_ACT, args)
+    target.load_state_dict(policy.state_dict())
+    opt = th.optim.AdamW(policy.parameters(), lr=args.lr)
+    graphs, rews, dones, bad = make_episode(B, T, profile, seed)
+    dones_m = ((1 - bad) * dones).view(T, B, 1)
+
+    def cycle():
+        h = policy.init_hidden().expand(B * U, -1)
+        hs, acts = [h], []
+        for t in range(T):
+            with th.no_grad():
+                q, h = policy(graphs[t], h)
+            acts.append(q.argmax(1, keepdim=True))
+            hs.append(h)
+        loss, _ = O.bptt_loss(policy, target, graphs, hs[0], hs[1], th.stack(acts), rews, dones_m, args.gamma,
+                              args.double_q, U)
+        opt.zero_grad()
+        loss.backward()
+        th.nn.utils.clip_grad_value_(policy.parameters(), clip_value=1)
+        opt.step()
+        with th.no_grad():
+            for p, pt in zip(policy.parameters(), target.parameters()):
+                pt.mul_(args.polyak).add_((1 - args.polyak) * p)
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        cycle()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cycle()
+    dt = time.perf_counter() - t0
+    return {"value": B * T * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} cycle(s) of {B} envs x T={T} steps (act x T + one BPTT update), torch CPU oracle, "
+                      f"{cores} threads, {dt:.1f} s", "seconds": dt}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    B, T = a.envs, min(a.cpu_T, a.T)
+    cpu = cpu_reference(B, T, a.profile, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * cpu["seconds"] / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, {B} envs, "
+                                   f"T={T} (bounded sample of T={a.T}), degree profile '{a.profile}'",
+                       "env_steps_per_step": B * T,
+                       "note": "reference's DGL-on-CPU path restated op-for-op in PyTorch (DGL 0.9.0 not installable)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=256, help="parallel env instances per GPU")
+    ap.add_argument("--T", type=int, default=50, help="sequence length = episode_limit of the exp3 maps")
+    ap.add_argument("--cpu-T", dest="cpu_T", type=int, default=4, help="timesteps of the bounded CPU sample")
+    ap.add_argument("--profile", default="full", choices=["full", "realistic", "random"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

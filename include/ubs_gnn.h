@@ -99,6 +99,41 @@ UBS_API int ubs_gru_gates_fwd(const float* gi, const float* gh, const float* h, 
 UBS_API int ubs_gru_gates_bwd(const float* gi, const float* gh, const float* h, const float* grad_out,
                       float* grad_gi, float* grad_gh, float* grad_h_direct, int64_t n, int H, void* stream);
 
+/* ---- Fused recurrent agent step / sequence -------------------------------------------------------------------
+ * Everything reference GnnAgent.forward does after the GATv2 relations (algos/madrqn/agents/gnn_agents.py:51-56):
+ * f_aggr Linear(Fin,H)+ReLU (:99,106-107) [UBS_STEP_AGGR], TarMAC.forward (:248-271) [UBS_STEP_TARMAC] or a plain
+ * GRUCell (:29,55; drqn gnn_agents.py:20,28), and the Linear Q head (:43-46).  One launch walks n_steps timesteps
+ * of every row tile (<= 16 agent rows = whole envs; envs never exchange data), hidden state resident on chip.
+ *   xin    (n_steps, n_rows, Fin)   [x_gt | x_ubs] (Fin = 2H) with AGGR, else the H-wide encoder output
+ *   h0     (n_rows, H)              hidden state entering step 0
+ *   mask   (n_steps, n_rows) uint32 talk-graph block masks (TARMAC), see ubs_block_attn_fwd
+ *   h_out  (n_steps, n_rows, H), q (n_steps, n_rows, A), actions (n_steps, n_rows) int64 argmax (nullable)
+ *   sv_*   saved activations for the backward (all NULL => inference):
+ *          sv_xc (n_steps,n_rows,H[+M]) [x | c], sv_vsq (.., round4(M+2K)), sv_alpha (.., U), sv_gate (.., 4H)
+ * `packed` comes from ubs_agent_pack (transposed + original copies of every weight, ubs_agent_pack_size floats)
+ * and must be rebuilt whenever a parameter changes.                                                            */
+#define UBS_STEP_AGGR 1
+#define UBS_STEP_TARMAC 2
+UBS_API int64_t ubs_agent_pack_size(int H, int M, int K, int A, int U, int Fin, int flags);
+UBS_API int ubs_agent_pack(int H, int M, int K, int A, int U, int Fin, int flags,
+                   const float* W_aggr, const float* b_aggr, const float* W_val, const float* b_val,
+                   const float* W_sign, const float* b_sign, const float* W_que, const float* b_que,
+                   const float* W_ih, const float* b_ih, const float* W_hh, const float* b_hh,
+                   const float* W_out, const float* b_out, float* packed, void* stream);
+UBS_API int ubs_agent_seq_fwd(int H, int M, int K, int A, int U, int Fin, int flags, const float* packed,
+                      const float* xin, const float* h0, const uint32_t* mask,
+                      float* h_out, float* q, int64_t* actions,
+                      float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
+                      int64_t n_rows, int n_steps, void* stream);
+/* Reverse-time walk.  dq (n_steps,n_rows,A) and dh_last (n_rows,H, nullable) come from the loss; outputs:
+ * d_xin (n_steps,n_rows,Fin), d_h0 (nullable) and the stashes st_dgi/st_dgh (.., 3H), st_dvsq (.., round4(M+2K)),
+ * st_dpre (.., H) from which the caller forms the parameter gradients with batched GEMMs over the whole sequence. */
+UBS_API int ubs_agent_seq_bwd(int H, int M, int K, int A, int U, int Fin, int flags, const float* packed,
+                      const float* h0, const float* h_out, const float* sv_xc, const float* sv_vsq,
+                      const float* sv_alpha, const float* sv_gate, const float* dq, const float* dh_last,
+                      float* d_xin, float* d_h0, float* st_dgi, float* st_dgh, float* st_dvsq, float* st_dpre,
+                      int64_t n_rows, int n_steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,84 @@
+"""CPU, world_size 2, gloo: flat-bucket gradient averaging == full-batch gradient; parameter broadcast."""
+import os
+import socket
+
+import pytest
+import torch as th
+import torch.distributed as td
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_model(seed):
+    th.manual_seed(seed)
+    return nn.Sequential(nn.Linear(6, 16), nn.Tanh(), nn.GRUCell(16, 8)) if False else nn.Sequential(
+        nn.Linear(6, 16), nn.Tanh(), nn.Linear(16, 3))
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from uav_bs_ctrl_b200 import dist
+    dist.init_from_env("gloo")
+    assert dist.world_size() == world and dist.rank() == rank
+    model = _make_model(seed=100 + rank)                # different init per rank on purpose
+    dist.sync_params(model)                             # ... rank 0's parameters win
+    bucket = dist.FlatGradBucket(model.parameters())
+    th.manual_seed(0)
+    x, y = th.randn(8, 6), th.randn(8, 3)               # global batch; rank r owns rows [4r, 4r+4)
+    xs, ys = x[4 * rank:4 * rank + 4], y[4 * rank:4 * rank + 4]
+    bucket.zero_()
+    nn.functional.mse_loss(model(xs), ys).backward()
+    bucket.rebind()
+    dist.avg_grads(bucket)
+    # module-level variant (per-call flatten) must agree
+    model2 = _make_model(seed=100)
+    nn.functional.mse_loss(model2(xs), ys).backward()
+    dist.avg_grads(model2)
+    mx = dist.all_reduce_max_scalar(float(rank + 1), "cpu")
+    th.save(dict(flat=bucket.flat.clone(), params=[p.detach().clone() for p in model.parameters()],
+                 flat2=th.cat([p.grad.reshape(-1) for p in model2.parameters()]), mx=mx),
+            os.path.join(out_dir, f"r{rank}.pt"))
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_flat_bucket_allreduce_matches_full_batch(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = th.load(tmp_path / "r0.pt"), th.load(tmp_path / "r1.pt")
+    ref = _make_model(seed=100)
+    for p, q0, q1 in zip(ref.parameters(), r0["params"], r1["params"]):
+        assert th.equal(p, q0) and th.equal(p, q1), "sync_params must broadcast rank 0's parameters"
+    th.manual_seed(0)
+    x, y = th.randn(8, 6), th.randn(8, 3)
+    nn.functional.mse_loss(ref(x), y).backward()        # equal shard sizes + mean loss => averaged grads == global grads
+    want = th.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    assert th.allclose(r0["flat"], want, rtol=1e-5, atol=1e-7) and th.equal(r0["flat"], r1["flat"])
+    assert th.allclose(r0["flat2"], want, rtol=1e-5, atol=1e-7)
+    assert r0["mx"] == r1["mx"] == 2.0
+
+
+def test_bucket_views_survive_zero_and_rebind():
+    from uav_bs_ctrl_b200 import dist
+    m = _make_model(0)
+    b = dist.FlatGradBucket(m.parameters())
+    m(th.randn(2, 6)).sum().backward()
+    g = th.cat([p.grad.reshape(-1) for p in m.parameters()])
+    assert th.equal(g, b.flat) and all(p.grad.data_ptr() >= b.flat.data_ptr() for p in m.parameters())
+    for p in m.parameters():
+        p.grad = None                                     # e.g. optimizer.zero_grad(set_to_none=True)
+    m(th.randn(2, 6)).sum().backward()
+    b.rebind()
+    assert th.equal(th.cat([p.grad.reshape(-1) for p in m.parameters()]), b.flat)
+    b.zero_()
+    assert float(b.flat.abs().sum()) == 0 and all(float(p.grad.abs().sum()) == 0 for p in m.parameters())

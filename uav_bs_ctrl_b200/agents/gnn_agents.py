@@ -133,11 +133,16 @@ class GraphObservationEncoder(nn.Module):
         })
         self.f_aggr = nn.Sequential(nn.Linear(len(self.f_conv) * out_feats, out_feats), nn.ReLU())
 
-    def forward(self, g, x):
+    def forward_relations(self, g, x):
+        """``[x_gt ‖ x_ubs]`` (N, 2H): the per-relation GATv2 outputs before the aggregator (the fused agent step
+        applies ``f_aggr`` itself)."""
         n = g.num_nodes("agent")
         x_gt = self.f_conv["seen"](g["seen"], (x["gt"], x["agent"])).view(n, -1)
         x_ubs = self.f_conv["near"](g["near"], (x["ubs"], x["agent"])).view(n, -1)
-        return self.f_aggr(th.cat((x_gt, x_ubs), 1))
+        return th.cat((x_gt, x_ubs), 1)
+
+    def forward(self, g, x):
+        return self.f_aggr(self.forward_relations(g, x))
 
 
 # ============================================================================================== comm protocols
@@ -291,11 +296,105 @@ class GnnAgent(nn.Module):
         else:
             raise KeyError("Unsupported communication scheme.")
         self.f_out = DuelingLayer(self._hidden_size, n_actions) if args.dueling else nn.Linear(self._hidden_size, n_actions)
+        self._n_actions = n_actions
+        self._msg_size, self._key_size = getattr(args, "msg_size", 0), getattr(args, "key_size", 0)
+        self._n_rounds = getattr(args, "n_rounds", 1)
+        self._pack_cache = {}
 
     def init_hidden(self):
         return th.zeros(1, self._hidden_size)
 
+    # ---- fused path (one kernel for aggregator + comm + GRU + Q head; whole sequences in one launch) -------------
+    def _fused_params(self):
+        p = {k: None for k in ops.PARAM_ORDER}
+        if isinstance(self.enc, GraphObservationEncoder):
+            p["W_aggr"], p["b_aggr"] = self.enc.f_aggr[0].weight, self.enc.f_aggr[0].bias
+        if self._comm_protocol == "tarmac":
+            c = self.f_comm
+            p.update(W_val=c.f_val.weight, b_val=c.f_val.bias, W_sign=c.f_sign.weight, b_sign=c.f_sign.bias,
+                     W_que=c.f_que.weight, b_que=c.f_que.bias)
+            cell = c.f_udt
+        else:
+            cell = self.rnn
+        p.update(W_ih=cell.weight_ih, b_ih=cell.bias_ih, W_hh=cell.weight_hh, b_hh=cell.bias_hh,
+                 W_out=self.f_out.weight, b_out=self.f_out.bias)
+        return p
+
+    def fused_dims(self, agents_per_env):
+        """``ops.AgentDims`` of the fused step for this agent, or ``None`` when the configuration is outside it
+        (other comm protocols, dueling head, multi-round TarMAC, > 16 agents per env)."""
+        if self._comm_protocol not in (None, "tarmac") or not isinstance(self.f_out, nn.Linear):
+            return None
+        if self._comm_protocol == "tarmac" and self._n_rounds != 1:
+            return None
+        graph_enc = isinstance(self.enc, GraphObservationEncoder)
+        flags = (ops.STEP_AGGR if graph_enc else 0) | (ops.STEP_TARMAC if self._comm_protocol == "tarmac" else 0)
+        H = self._hidden_size
+        if self._comm_protocol == "tarmac" and agents_per_env is None:
+            return None
+        d = ops.AgentDims(H, self._msg_size, self._key_size, self._n_actions, agents_per_env or 1,
+                          2 * H if graph_enc else H, flags)
+        return d if d.supported() else None
+
+    def _packed(self, dims, params):
+        key = tuple((t.data_ptr(), t._version) for t in params.values() if t is not None)
+        hit = self._pack_cache.get(dims.ints())
+        if hit is None or hit[0] != key:
+            buf = ops.agent_pack(dims, params, None if hit is None else hit[1])
+            self._pack_cache[dims.ints()] = (key, buf)
+            return buf
+        return hit[1]
+
+    def _encode_pre(self, g):
+        """Input of the fused step: ``[x_gt ‖ x_ubs]`` for the graph encoder (aggregator fused), else the encoder output."""
+        if isinstance(self.enc, GraphObservationEncoder):
+            return self.enc.forward_relations(g, g.ndata["feat"])
+        return self.enc(g, g.ndata["feat"]).view(g.num_nodes("agent"), -1)
+
+    def _talk_mask(self, g):
+        if self._comm_protocol != "tarmac":
+            return None, None
+        blk = g["talk"].block_mask()
+        return (None, None) if blk is None else blk
+
+    def can_fuse(self, g):
+        return self.fused_dims(self._talk_mask(g)[0]) is not None
+
+    def forward_sequence(self, graphs, h0):
+        """``T`` timesteps in one go: ``graphs`` is a list of T batched observation graphs with the same agent
+        rows (or ONE graph that already is their ``batch`` plus ``T`` inferred from ``h0``).  Returns
+        ``(q (T,N,A), h_last (N,H))`` — identical math to calling ``forward`` T times (the encoder does not depend on
+        ``h``, reference ``gnn_agents.py:53``), but the encoder runs once over all T·N agent rows and the recurrent
+        part is one persistent kernel forward and one backward."""
+        from ..graph import batch as graph_batch
+        gb = graph_batch(list(graphs)) if isinstance(graphs, (list, tuple)) else graphs
+        N = h0.shape[0]
+        TN = gb.num_nodes("agent")
+        T = TN // N
+        block, mask = self._talk_mask(gb)
+        dims = self.fused_dims(block)
+        if dims is None:
+            raise NotImplementedError("forward_sequence needs the fused configuration (c in {None,'tarmac'}, Linear head)")
+        params = self._fused_params()
+        packed = self._packed(dims, params)
+        xin = self._encode_pre(gb).view(T, N, dims.Fin)
+        h0 = h0.contiguous()
+        if th.is_grad_enabled() and (xin.requires_grad or any(p is not None and p.requires_grad for p in params.values())):
+            q, h_last, _ = ops.AgentSequence.apply(xin, h0, None if mask is None else mask.view(T, N), dims, packed,
+                                                   *[params[k] for k in ops.PARAM_ORDER])
+            return q, h_last
+        q, h_all = ops.agent_seq_infer(dims, packed, xin, h0, mask)
+        return q, h_all[T - 1]
+
     def forward(self, g, h):
+        if not th.is_grad_enabled() and h.is_cuda:
+            block, mask = self._talk_mask(g)
+            dims = self.fused_dims(block)
+            if dims is not None:
+                packed = self._packed(dims, self._fused_params())
+                xin = self._encode_pre(g).unsqueeze(0)
+                q, h_all = ops.agent_seq_infer(dims, packed, xin, h.contiguous(), mask)
+                return q[0], h_all[0]
         x = self.enc(g, g.ndata["feat"]).view(g.num_nodes("agent"), -1)
         h = self.f_comm(g["talk"], x, h) if self._comm_protocol is not None else self.rnn(x, h)
         return self.f_out(h), h

@@ -45,8 +45,9 @@ def build_obs_graph_batch(agent_obs: th.Tensor, gt_obs: th.Tensor, ubs_obs: th.T
     B, U = agent_obs.shape[:2]
     N = B * U
     dev = agent_obs.device
-    x_gt, ip_gt, _ = _star(gt_obs[..., 0].reshape(N, -1) == 1, gt_obs[..., 1:].reshape(N, gt_obs.shape[2], -1), N)
-    x_ubs, ip_ubs, _ = _star(ubs_obs[..., 0].reshape(N, -1) == 1, ubs_obs[..., 1:].reshape(N, ubs_obs.shape[2], -1), N)
+    Gn, Un = gt_obs.shape[2], ubs_obs.shape[2]
+    x_gt, ip_gt, _ = _star(gt_obs[..., 0].reshape(N, Gn) == 1, gt_obs[..., 1:].reshape(N, Gn, gt_obs.shape[3] - 1), N)
+    x_ubs, ip_ubs, _ = _star(ubs_obs[..., 0].reshape(N, Un) == 1, ubs_obs[..., 1:].reshape(N, Un, ubs_obs.shape[3] - 1), N)
     E_gt, E_ubs = x_gt.shape[0], x_ubs.shape[0]
     src, dst, csr = {}, {}, {}
     c_seen, c_near, c_talk = OBS_CETS[1], OBS_CETS[2], OBS_CETS[0]

@@ -569,7 +569,10 @@ def batch(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
         else:
             eid = th.cat([(p.eid if p.eid is not None else th.arange(p.n_edges, device=dev)) + eoff[i]
                           for i, p in enumerate(parts)])
-        csr[c] = RelCSR(indptr, src_idx, eid, nn_[st], nn_[dt], acc)
+        blk, msk = None, None
+        if st == dt and all(p.mask is not None and p.block == parts[0].block for p in parts):
+            blk, msk = parts[0].block, th.cat([p.mask for p in parts])   # block-diagonal form composes by concat
+        csr[c] = RelCSR(indptr, src_idx, eid, nn_[st], nn_[dt], acc, blk, msk)
     nframes = {t: _cat_frames([g._nframes[t] for g in graphs], [g._nn[t] for g in graphs], f"node[{t}]")
                for t in g0._ntypes}
     eframes = {c: _cat_frames([g._eframes[c] for g in graphs], [g._ne(c) for g in graphs],

@@ -98,6 +98,7 @@ class MultiAgentQLearner:
         if self.anneal_lr:
             self.lr_scheduler = th.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=lambda e: max(0.4, 1 - e / 100))
         self.double_q = args.double_q
+        self.fused = bool(getattr(args, "fused", True))      # sequence-fused update (False: per-step module calls)
 
     # ------------------------------------------------------------------------------------------ acting
     def init_hidden(self, batch_size=1):
@@ -148,6 +149,13 @@ class MultiAgentQLearner:
         """Reference ``learner.py:118-129``: T policy steps with grad + T target steps without + one more policy step."""
         agent_out, target_out = [], []
         T = self.max_seq_len
+        can_fuse = getattr(self.policy_net, "can_fuse", None)
+        if self.fused and can_fuse is not None and can_fuse(obs[0]) and h.is_cuda:
+            # same math, but the encoder runs once over all timesteps and the recurrence is one persistent kernel
+            agent_out, _ = self.policy_net.forward_sequence(obs, h)
+            with th.no_grad():
+                target_out, _ = self.target_net.forward_sequence(obs[1:], h_targ)
+            return agent_out, target_out
         for t in range(T):
             logits, h = self.policy_net(obs[t], h)
             agent_out.append(logits)

@@ -216,3 +216,135 @@ def gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
     gi = th.addmm(b_ih, x, w_ih.t()) if b_ih is not None else x @ w_ih.t()
     gh = th.addmm(b_hh, h, w_hh.t()) if b_hh is not None else h @ w_hh.t()
     return GRUGates.apply(gi, gh, h)
+
+
+# ====================================================================================================================
+# Fused recurrent agent sequence (ubs_agent_pack / ubs_agent_seq_fwd / ubs_agent_seq_bwd)
+STEP_AGGR, STEP_TARMAC = 1, 2
+PARAM_ORDER = ("W_aggr", "b_aggr", "W_val", "b_val", "W_sign", "b_sign", "W_que", "b_que", "W_ih", "b_ih", "W_hh",
+               "b_hh", "W_out", "b_out")
+
+
+class AgentDims:
+    """Shape of the fused step: hidden H, message M, key K, actions A, agents per env U, input width Fin, flags."""
+
+    def __init__(self, H, M, K, A, U, Fin, flags):
+        self.H, self.M, self.K, self.A, self.U, self.Fin, self.flags = H, M, K, A, U, Fin, flags
+        self.tarmac, self.aggr = bool(flags & STEP_TARMAC), bool(flags & STEP_AGGR)
+        self.V = (M + 2 * K) if self.tarmac else 0
+        self.Vp = (self.V + 3) // 4 * 4
+        self.I = H + M if self.tarmac else H
+
+    def ints(self):
+        return (self.H, self.M, self.K, self.A, self.U, self.Fin, self.flags)
+
+    def supported(self):
+        ok = self.H % 4 == 0 and 16 <= self.H <= 256 and 1 <= self.A <= 64
+        if self.tarmac:
+            ok = ok and 1 <= self.U <= 16 and self.M % 4 == 0 and self.M >= 4 and self.K >= 1
+        ok = ok and ((self.Fin % 4 == 0 and self.Fin >= 4) if self.aggr else self.Fin == self.H)
+        return ok
+
+
+def agent_pack(dims: AgentDims, params: dict, out=None):
+    """Builds the packed weight buffer (transposed copies for the forward GEMMs + originals for the backward)."""
+    lib = _lib.load()
+    n = int(lib.ubs_agent_pack_size(*dims.ints()))
+    dev = params["W_ih"].device
+    if out is None or out.numel() != n:
+        out = th.empty(n, dtype=th.float32, device=dev)
+    ptrs = [_lib.ptr(_f32c(params.get(k).detach()) if params.get(k) is not None else None) for k in PARAM_ORDER]
+    _lib.check(lib.ubs_agent_pack(*dims.ints(), *ptrs, _lib.ptr(out), _lib.stream()), "ubs_agent_pack")
+    return out
+
+
+def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False):
+    """Inference: ``xin (T,N,Fin)``, ``h0 (N,H)`` -> ``q (T,N,A)``, ``h_out (T,N,H)`` [, greedy actions (T,N) int64]."""
+    lib = _lib.load()
+    _lib.require_cuda(xin, h0, packed)
+    xin, h0 = _f32c(xin), _f32c(h0)
+    T, N = xin.shape[0], xin.shape[1]
+    h_out = th.empty(T, N, dims.H, dtype=th.float32, device=xin.device)
+    q = th.empty(T, N, dims.A, dtype=th.float32, device=xin.device)
+    acts = th.empty(T, N, dtype=th.int64, device=xin.device) if want_actions else None
+    with _timed("agent_seq_fwd", (T, N, dims.ints(), False)):
+        _lib.check(lib.ubs_agent_seq_fwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(xin), _lib.ptr(h0), _lib.ptr(mask),
+                                         _lib.ptr(h_out), _lib.ptr(q), _lib.ptr(acts), None, None, None, None,
+                                         N, T, _lib.stream()), "ubs_agent_seq_fwd")
+    return (q, h_out, acts) if want_actions else (q, h_out)
+
+
+class AgentSequence(th.autograd.Function):
+    """Whole-sequence forward / backward of the recurrent part of the agent.
+
+    ``forward(xin (T,N,Fin), h0 (N,H), mask (T,N) int32|None, dims, packed, *params[PARAM_ORDER])``
+    returns ``(q (T,N,A), h_last (N,H), h_all (T,N,H) [non-differentiable])``.  The backward walks the sequence in
+    reverse inside one kernel and forms every parameter gradient with batched library GEMMs over all T·N rows."""
+
+    @staticmethod
+    def forward(ctx, xin, h0, mask, dims, packed, *params):
+        lib = _lib.load()
+        _lib.require_cuda(xin, h0, packed)
+        xin, h0 = _f32c(xin), _f32c(h0)
+        T, N = xin.shape[0], xin.shape[1]
+        dev = xin.device
+        f32 = dict(dtype=th.float32, device=dev)
+        h_out = th.empty(T, N, dims.H, **f32)
+        q = th.empty(T, N, dims.A, **f32)
+        sv_xc = th.empty(T, N, dims.I, **f32)
+        sv_gate = th.empty(T, N, 4 * dims.H, **f32)
+        sv_vsq = th.empty(T, N, dims.Vp, **f32) if dims.tarmac else None
+        sv_alpha = th.empty(T, N, dims.U, **f32) if dims.tarmac else None
+        with _timed("agent_seq_fwd", (T, N, dims.ints(), True)):
+            _lib.check(lib.ubs_agent_seq_fwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(xin), _lib.ptr(h0), _lib.ptr(mask),
+                                             _lib.ptr(h_out), _lib.ptr(q), None, _lib.ptr(sv_xc), _lib.ptr(sv_vsq),
+                                             _lib.ptr(sv_alpha), _lib.ptr(sv_gate), N, T, _lib.stream()),
+                       "ubs_agent_seq_fwd")
+        ctx.dims = dims
+        ctx.has = [p is not None for p in params]
+        ctx.save_for_backward(xin, h0, packed, h_out, sv_xc, sv_vsq, sv_alpha, sv_gate)
+        ctx.mark_non_differentiable(h_out)
+        return q, h_out[T - 1].clone(), h_out
+
+    @staticmethod
+    def backward(ctx, dq, dh_last, _dh_all):
+        xin, h0, packed, h_out, sv_xc, sv_vsq, sv_alpha, sv_gate = ctx.saved_tensors
+        dims = ctx.dims
+        lib = _lib.load()
+        T, N = xin.shape[0], xin.shape[1]
+        H, M, K, A, I, V, Vp = dims.H, dims.M, dims.K, dims.A, dims.I, dims.V, dims.Vp
+        f32 = dict(dtype=th.float32, device=xin.device)
+        dq = _f32c(dq) if dq is not None else th.zeros(T, N, A, **f32)
+        dh_last = _f32c(dh_last) if dh_last is not None else None
+        d_xin = th.empty_like(xin)
+        d_h0 = th.empty_like(h0) if ctx.needs_input_grad[1] else None
+        st_dgi, st_dgh = th.empty(T, N, 3 * H, **f32), th.empty(T, N, 3 * H, **f32)
+        st_dvsq = th.empty(T, N, Vp, **f32) if dims.tarmac else None
+        st_dpre = th.empty(T, N, H, **f32) if dims.aggr else None
+        with _timed("agent_seq_bwd", (T, N, dims.ints(), True)):
+            _lib.check(lib.ubs_agent_seq_bwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(h0), _lib.ptr(h_out),
+                                             _lib.ptr(sv_xc), _lib.ptr(sv_vsq), _lib.ptr(sv_alpha), _lib.ptr(sv_gate),
+                                             _lib.ptr(dq), _lib.ptr(dh_last), _lib.ptr(d_xin), _lib.ptr(d_h0),
+                                             _lib.ptr(st_dgi), _lib.ptr(st_dgh), _lib.ptr(st_dvsq), _lib.ptr(st_dpre),
+                                             N, T, _lib.stream()), "ubs_agent_seq_bwd")
+        # parameter gradients: batched fp32 library GEMMs over all T*N rows
+        TN = T * N
+        xc, dgi, dgh = sv_xc.view(TN, I), st_dgi.view(TN, 3 * H), st_dgh.view(TN, 3 * H)
+        hprev = th.cat((h0.unsqueeze(0), h_out[:-1]), 0).view(TN, H)
+        g = {}
+        g["W_ih"], g["b_ih"] = dgi.t() @ xc, dgi.sum(0)
+        g["W_hh"], g["b_hh"] = dgh.t() @ hprev, dgh.sum(0)
+        dq2 = dq.view(TN, A)
+        g["W_out"], g["b_out"] = dq2.t() @ h_out.view(TN, H), dq2.sum(0)
+        if dims.tarmac:
+            dv = st_dvsq.view(TN, Vp)
+            gw = th.cat((dv.t() @ xc[:, :H], dv.t() @ hprev), 1)           # (Vp, 2H) for inputs [x ‖ h]
+            gb = dv.sum(0)
+            g["W_val"], g["b_val"] = gw[:M], gb[:M]
+            g["W_sign"], g["b_sign"] = gw[M:M + K], gb[M:M + K]
+            g["W_que"], g["b_que"] = gw[M + K:V], gb[M + K:V]
+        if dims.aggr:
+            dp = st_dpre.view(TN, H)
+            g["W_aggr"], g["b_aggr"] = dp.t() @ xin.view(TN, dims.Fin), dp.sum(0)
+        grads = tuple(g.get(k) if has else None for k, has in zip(PARAM_ORDER, ctx.has))
+        return (d_xin if ctx.needs_input_grad[0] else None, d_h0, None, None, None) + grads

@@ -131,6 +131,35 @@ def train_cycle(learner, obs, rews, dones, bad, T, B, eps, host_io, acts_host=No
     return learner.update(samples=[learner.buffer.memory[-1]], sync=host_io)
 
 
+def train_cycle_arena(learner, arena, packets, T, eps, host_io, acts_host=None):
+    """Same step on the packed path: observations are packets staged into the sequence arena (ONE copy each), act is
+    three kernels per vector-step (optionally a replayed CUDA graph), update reads the arena in place."""
+    learner.begin_sequence(arena)
+    if host_io:
+        arena.load(0, packets[0])
+    for t in range(T):
+        acts = learner.act_arena(arena, t, eps)
+        if host_io:
+            acts_host[t].copy_(acts, non_blocking=True)
+            th.cuda.current_stream().synchronize()           # the env needs the actions before it can step
+            arena.load(t + 1, packets[t + 1])                 # next observation (+ reward / done) arrives
+    return learner.update_arena(arena, sync=host_io)
+
+
+def make_packets(B, T, profile, seed, pin):
+    from uav_bs_ctrl_b200.arena import PacketLayout, ObsPacket
+    from uav_bs_ctrl_b200.synth import synth_dense_obs
+    L = PacketLayout(B, U, G)
+    gen = th.Generator().manual_seed(seed + 7919)
+    out = []
+    for t in range(T + 1):
+        a, gt, ubs, adj = synth_dense_obs(B, U, G, profile, seed=seed + t)
+        done = th.ones(B) if t == T else th.zeros(B)       # episode_limit reached on the last step (bad_mask mutes it)
+        out.append(ObsPacket(L, pin=pin).fill_from_dense(a, gt, ubs, adj, rew=th.rand(B, U, generator=gen),
+                                                         done=done, bad=done))
+    return L, out
+
+
 def algorithmic_bytes_gat(meta):
     """star-layout GATv2 relation.  fwd 4(E·F_s + N·F_d + N+1 + N·H) + 4P (+8·N·heads when stats are
     saved); bwd 4(E·F_s + N·F_d + N+1 + 2N·H + 2N·heads) + 8P."""
@@ -155,12 +184,23 @@ def run_ours(a):
     th.manual_seed(0)
     learner = MultiAgentQLearner(dict(obs_shape=OBS_SHAPE, state_shape=None, n_actions=N_ACT, n_agents=U,
                                       episode_limit=T), model_args(dev, T, B))
-    graphs, rews, dones, bad = make_episode(B, T, a.profile, seed=1234 + 100 * rank)
-    h2d = sum(graph_bytes(g) for g in graphs) + rews.numel() * 4 + dones.numel() * 8
-    d2h = T * B * U * 8 + 4 + T * B * U * 4
-    dev_graphs = [g.to(dev) for g in graphs]
-    dev_rews, dev_dones, dev_bad = rews.to(dev), dones.to(dev), bad.to(dev)
     eps = 0.05
+    d2h = T * B * U * 8 + 4 + T * B * U * 4
+    use_arena = a.path == "arena"
+    if use_arena:
+        learner.args.cuda_graphs = not a.no_graphs
+        layout, packets = make_packets(B, T, a.profile, seed=1234 + 100 * rank, pin=True)
+        h2d = (T + 1) * layout.words * 4
+        arena = learner.new_arena(G)
+        for t in range(T + 1):
+            arena.load(t, packets[t])
+        value_step = lambda: train_cycle_arena(learner, arena, None, T, eps, False)
+    else:
+        graphs, rews, dones, bad = make_episode(B, T, a.profile, seed=1234 + 100 * rank)
+        h2d = sum(graph_bytes(g) for g in graphs) + rews.numel() * 4 + dones.numel() * 8
+        dev_graphs = [g.to(dev) for g in graphs]
+        dev_rews, dev_dones, dev_bad = rews.to(dev), dones.to(dev), bad.to(dev)
+        value_step = lambda: train_cycle(learner, dev_graphs, dev_rews, dev_dones, dev_bad, T, B, eps, False)
 
     def barrier():
         if world > 1:
@@ -187,26 +227,30 @@ def run_ours(a):
         return ms, launches, clocks
 
     # ---- value: inputs resident in HBM
-    ms, launches, clocks = timed(lambda: train_cycle(learner, dev_graphs, dev_rews, dev_dones, dev_bad, T, B, eps, False),
-                                 a.steps, a.warmup, sample_clocks=True)
+    ms, launches, clocks = timed(value_step, a.steps, a.warmup, sample_clocks=True)
     value = world * B * T * a.steps / (ms * 1e-3)
 
     # ---- e2e: pinned host observations in, actions / loss / q-values out, every step
     e2e = None
     if not a.no_e2e:
-        pin_graphs = [g.pin_memory() for g in graphs]
-        pin_rews, pin_dones, pin_bad = rews.pin_memory(), dones.pin_memory(), bad.pin_memory()
         acts_host = th.empty(T, B * U, dtype=th.int64).pin_memory()
-        ms_e, _, _ = timed(lambda: train_cycle(learner, pin_graphs, pin_rews, pin_dones, pin_bad, T, B, eps, True,
-                                               acts_host), a.steps, max(1, a.warmup // 2 + 1))
+        if use_arena:
+            e2e_step = lambda: train_cycle_arena(learner, arena, packets, T, eps, True, acts_host)
+        else:
+            pin_graphs = [g.pin_memory() for g in graphs]
+            pin_rews, pin_dones, pin_bad = rews.pin_memory(), dones.pin_memory(), bad.pin_memory()
+            e2e_step = lambda: train_cycle(learner, pin_graphs, pin_rews, pin_dones, pin_bad, T, B, eps, True, acts_host)
+        ms_e, _, _ = timed(e2e_step, a.steps, max(1, a.warmup // 2 + 1))
         e2e = {"value": world * B * T * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps}
 
     # ---- roofline of the dominant kernel: CUDA events around every C-ABI call during one extra step
     roofline = None
     if rank == 0:
+        if use_arena:
+            learner.args.cuda_graphs = False             # replayed graphs bypass the Python-side event hooks
         ops.TIMER = ops.KernelTimer()
-        train_cycle(learner, dev_graphs, dev_rews, dev_dones, dev_bad, T, B, eps, False)
+        value_step()
         summ = ops.TIMER.summary()
         ops.TIMER = None
         dom = max(summ, key=lambda k: summ[k]["ms"])
@@ -249,7 +293,8 @@ def run_ours(a):
                 "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, "
                                        f"{B} envs/GPU, T={T}, degree profile '{a.profile}'",
                            "env_steps_per_step": world * B * T, "update_batch": f"{B} sequences x {T} per GPU",
-                           "parallelism": f"dp{world}", "l2_policy": "inputs exceed L2: "
+                           "parallelism": f"dp{world}", "path": a.path + ("" if a.no_graphs or a.path != "arena" else "+cudagraphs"),
+                           "l2_policy": "inputs exceed L2: "
                            f"{h2d / 2**20:.0f} MiB of observations are streamed per step (> 126 MB L2)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": int(launches)}
@@ -332,6 +377,9 @@ def main():
     ap.add_argument("--T", type=int, default=50, help="sequence length = episode_limit of the exp3 maps")
     ap.add_argument("--cpu-T", dest="cpu_T", type=int, default=4, help="timesteps of the bounded CPU sample")
     ap.add_argument("--profile", default="full", choices=["full", "realistic", "random"])
+    ap.add_argument("--path", default="arena", choices=["arena", "graph"],
+                    help="arena: packed packets + sequence arena (+ CUDA graphs); graph: reference-shaped graph objects")
+    ap.add_argument("--no-graphs", action="store_true", help="arena path without CUDA-graph replay of the act step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

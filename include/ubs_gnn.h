@@ -75,6 +75,26 @@ UBS_API int ubs_gatv2_bwd(const float* x_src, const float* x_dst, const int32_t*
                   int64_t n_dst, int64_t n_edges, int64_t n_src, int F_s, int F_d, int heads, int D,
                   float negative_slope, int flags, void* stream);
 
+/* Strided-segment variants: the same kernels over n_seg graphs laid out at fixed strides (one per timestep of a
+ * sequence arena), in ONE launch.  Segment s reads x_src + s*st_xsrc, x_dst + s*st_xdst, indptr + s*st_ip (segment-
+ * local offsets), src_idx + s*st_sidx (strides in elements); destination v of segment s is output row s*n_dst_seg + v
+ * with row stride ld_out (so two relations can write the two halves of one (rows, 2H) buffer); smax / ssum rows
+ * likewise.  n_edges is only a hint (mean degree) for the launch shape.                                          */
+UBS_API int ubs_gatv2_seg_fwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                      const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                      const float* attn, const float* W_res, const float* b_res,
+                      float* out, float* smax, float* ssum, int64_t n_seg, int64_t n_dst_seg, int64_t n_edges,
+                      int64_t st_xsrc, int64_t st_xdst, int64_t st_ip, int64_t st_sidx, int64_t ld_out,
+                      int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
+UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                      const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                      const float* attn, const float* W_res, const float* b_res,
+                      const float* out, const float* grad_out, const float* smax, const float* ssum,
+                      float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                      int64_t n_seg, int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst,
+                      int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout,
+                      int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
+
 /* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
  * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
  * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.

@@ -1,0 +1,157 @@
+"""Host logic of the packed observation packets / sequence arena (CPU) and their GPU parity with the graph path."""
+from types import SimpleNamespace
+
+import pytest
+import torch as th
+
+from uav_bs_ctrl_b200.arena import PacketLayout, ObsPacket, SequenceArena, packet_graph
+from uav_bs_ctrl_b200.builder import build_obs_graph_batch
+from uav_bs_ctrl_b200.synth import synth_dense_obs
+from helpers import assert_close
+
+SHAPE = {'agent': 2, 'ubs': 2, 'gt': 4}
+
+
+def test_layout_sections_are_aligned_and_disjoint():
+    L = PacketLayout(5, 3, 7)
+    ends = 0
+    for name in ("x_gt", "x_ubs", "x_agent", "ip_seen", "ip_near", "mask", "rew", "done", "bad"):
+        assert L.off[name] % 4 == 0 and L.off[name] >= ends
+        ends = L.off[name] + L.size[name]
+    assert L.words % 4 == 0 and L.words >= ends
+    assert L.size["x_gt"] == 5 * 3 * 7 * 4 and L.size["ip_seen"] == 16
+
+
+@pytest.mark.parametrize("profile,comm_p", [("full", 1.0), ("realistic", 0.5), ("random", 0.3)])
+def test_packet_graph_equals_builder_graph(profile, comm_p):
+    B, U, G = 4, 5, 6
+    a, gt, ubs, adj = synth_dense_obs(B, U, G, profile, seed=2, comm_p=comm_p, near_p=0.6)
+    ref = build_obs_graph_batch(a, gt, ubs, adj)
+    pk = ObsPacket(PacketLayout(B, U, G)).fill_from_dense(a, gt, ubs, adj, rew=th.ones(B, U), done=th.zeros(B))
+    g = pk.to_graph()
+    for nt in ("agent", "gt", "ubs"):
+        assert th.equal(g.nodes[nt].data["feat"], ref.nodes[nt].data["feat"])
+    for et in ("seen", "near", "talk"):
+        assert th.equal(g[et].csr().indptr, ref[et].csr().indptr)
+        assert th.equal(g[et].csr().src_of_slot(), ref[et].csr().src_of_slot())
+        (u1, v1), (u2, v2) = g.edges(et), ref.edges(et)
+        assert th.equal(u1, u2) and th.equal(v1, v2), et
+    assert th.equal(g["talk"].block_mask()[1], ref["talk"].block_mask()[1])
+    assert g.batch_size == B and g.uniform_block("agent") == U
+
+
+def test_arena_load_and_reward_bookkeeping():
+    B, U, G, T = 3, 2, 4, 3
+    L = PacketLayout(B, U, G)
+    ar = SequenceArena(L, T + 1, hidden=8, device="cpu")
+    for t in range(T + 1):
+        a, gt, ubs, adj = synth_dense_obs(B, U, G, "realistic", seed=t)
+        done = th.tensor([0., 1., 0.]) if t == 2 else th.zeros(B)
+        bad = th.tensor([0., 1., 0.]) if t == 2 else th.zeros(B)
+        ar.load(t, ObsPacket(L).fill_from_dense(a, gt, ubs, adj, rew=th.full((B, U), float(t)), done=done, bad=bad))
+    assert ar.rewards(T).shape == (T, B, U) and float(ar.rewards(T)[1].mean()) == 2.0     # reward of transition 1 sits in slot 2
+    assert ar.dones(T).shape == (T, B, 1) and float(ar.dones(T).sum()) == 0.0                # done muted by bad_mask
+    g = ar.graph(1)
+    a, gt, ubs, adj = synth_dense_obs(B, U, G, "realistic", seed=1)
+    assert th.equal(g.nodes["gt"].data["feat"], build_obs_graph_batch(a, gt, ubs, adj).nodes["gt"].data["feat"])
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+def _learner(B, U, T, fused=True, graphs=False, seed=0):
+    from uav_bs_ctrl_b200.learner import MultiAgentQLearner
+    th.manual_seed(seed)
+    a = SimpleNamespace(device="cuda", o="gnn", c="tarmac", share_reward=False, hidden_size=64, n_layers=1, n_heads=4,
+                        msg_size=64, key_size=16, n_rounds=1, lr=1e-3, gamma=0.99, polyak=0.9, batch_size=1,
+                        replay_size=2, max_seq_len=T, anneal_lr=False, double_q=True, dueling=False, mixer=False,
+                        n_envs=B, fused=fused, cuda_graphs=graphs)
+    return MultiAgentQLearner(dict(obs_shape=SHAPE, state_shape=None, n_actions=9, n_agents=U, episode_limit=T), a)
+
+
+def _episode(B, U, G, T, seed=50):
+    L = PacketLayout(B, U, G)
+    gen = th.Generator().manual_seed(seed)
+    pk = []
+    for t in range(T + 1):
+        a, gt, ubs, adj = synth_dense_obs(B, U, G, "realistic", seed=seed + t, comm_p=0.7)
+        done = th.zeros(B)
+        if t == T:
+            done[:] = 1.0
+        pk.append(ObsPacket(L).fill_from_dense(a, gt, ubs, adj, rew=th.rand(B, U, generator=gen), done=done, bad=done))
+    return L, pk
+
+
+@pytest.mark.gpu
+def test_arena_step_and_sequence_match_graph_path():
+    B, U, G, T = 6, 8, 30, 4
+    Lr = _learner(B, U, T)
+    layout, pk = _episode(B, U, G, T)
+    ar = Lr.new_arena(G)
+    for t in range(T + 1):
+        ar.load(t, pk[t])
+    net = Lr.policy_net
+    graphs = [p.to_graph().to("cuda") for p in pk]
+    h = th.randn(B * U, 64, device="cuda") * 0.2
+    ar.h[0].copy_(h)
+    with th.no_grad():
+        for t in range(T + 1):
+            q_a = net.arena_step(ar, t)
+            q_g, h = net(graphs[t], h)
+            # same kernels, but the lane-group width of the relation kernel is picked from the (capacity vs actual)
+            # edge-count hint, so sums may associate differently: tight tolerance instead of bitwise equality
+            assert_close(q_a, q_g, rtol=1e-5, atol_scale=1e-6, what=f"q[{t}]")
+            assert_close(ar.h[t + 1], h, rtol=1e-5, atol_scale=1e-6, what=f"h[{t}]")
+            assert th.equal(ar.acts[t], q_a.argmax(1))
+            h = ar.h[t + 1].clone()
+    # training: arena sequence vs list-of-graphs sequence
+    h0 = ar.h[0].clone()
+    q1, _ = net.arena_sequence(ar, 0, T + 1, h0)
+    (q1 ** 2).mean().backward()
+    g1 = [p.grad.clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    q2, _ = net.forward_sequence(graphs, h0)
+    (q2 ** 2).mean().backward()
+    assert_close(q1, q2, rtol=1e-5, atol_scale=1e-6, what="q")
+    gmax = max(float(p.grad.abs().max()) for p in net.parameters())
+    for a, p in zip(g1, net.parameters()):
+        assert float((a - p.grad).abs().max()) <= 1e-5 * float(p.grad.abs().max()) + 1e-7 * gmax, "param grad"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_learner_arena_cycle_matches_graph_object_cycle(use_graphs):
+    B, U, G, T = 5, 8, 20, 4
+    layout, pk = _episode(B, U, G, T, seed=70)
+    # (1) graph-object API (reference-shaped act / cache / update)
+    L1 = _learner(B, U, T, graphs=False, seed=3)
+    graphs = [p.to_graph().to("cuda") for p in pk]
+    h = L1.init_hidden(B).to("cuda")
+    acts_1 = []
+    for t in range(T):
+        acts, h2 = L1.act(graphs[t], h, 0.0)                          # greedy: no RNG in the comparison
+        rew, done = pk[t + 1].sec("rew").view(B, U).cuda(), pk[t + 1].sec("done").cuda()
+        L1.cache(graphs[t], h, None, acts, rew, graphs[t + 1], h2, None, done, pk[t + 1].sec("bad").cuda())
+        acts_1.append(acts)
+        h = h2
+    out1 = L1.update(samples=[L1.buffer.memory[-1]])
+    g1 = L1.grad_bucket.flat.clone()
+    # (2) arena API, two consecutive cycles (the second one replays captured graphs when enabled)
+    L2 = _learner(B, U, T, graphs=use_graphs, seed=3)
+    ar = L2.new_arena(G)
+    for cycle in range(2):
+        L2.begin_sequence(ar)
+        for t in range(T + 1):
+            ar.load(t, pk[t])
+        for t in range(T):
+            acts = L2.act_arena(ar, t, 0.0)
+            if cycle == 0:
+                assert float((acts != acts_1[t]).float().mean()) < 0.01      # argmax ties / 1e-6 differences only
+        if cycle == 0:
+            out2 = L2.update_arena(ar)
+            g2 = L2.grad_bucket.flat.clone()
+    assert abs(out1["LossQ"] - out2["LossQ"]) <= 1e-5 * abs(out1["LossQ"])
+    assert_close(g2, g1, rtol=1e-4, atol_scale=1e-5, what="policy gradients")
+    # after the update the act path must see the new weights (packed buffer refreshed, graphs still valid)
+    with th.no_grad():
+        q_ref, _ = L2.policy_net(graphs[0], th.zeros(B * U, 64, device="cuda"))
+    assert float((ar.acts[0] != q_ref.argmax(1)).float().mean()) < 0.01

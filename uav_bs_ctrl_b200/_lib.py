@@ -33,6 +33,8 @@ _PROTOS = {
                                      _i64, _int, _int, _int, _flt, _ptr]),
     "ubs_gru_gates_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
+    "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),
+    "ubs_gatv2_seg_bwd": (C.c_int, [_F] * 19 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
     "ubs_agent_pack_size": (_i64, [_int] * 7),
     "ubs_agent_pack": (C.c_int, [_int] * 7 + [_F] * 15 + [_ptr]),
     "ubs_agent_seq_fwd": (C.c_int, [_int] * 7 + [_F] * 11 + [_i64, _int, _ptr]),

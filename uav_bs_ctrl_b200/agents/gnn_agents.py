@@ -386,6 +386,56 @@ class GnnAgent(nn.Module):
         q, h_all = ops.agent_seq_infer(dims, packed, xin, h0, mask)
         return q, h_all[T - 1]
 
+    # ---- sequence-arena path: no graph objects at all (arena.py) ---------------------------------------------------
+    def _arena_xin(self, arena, t0, T):
+        """``[x_gt ‖ x_ubs] (T, N, 2H)`` for arena slots ``t0 .. t0+T-1``: ONE strided-segment launch per relation."""
+        L, W = arena.layout, arena.layout.words
+        convs = (self.enc.f_conv["seen"], self.enc.f_conv["near"])
+        specs = [ops.RelSpec(arena.ptr("x_gt", t0), W, L.F_gt, arena.ptr("ip_seen", t0), W, T * L.cap_gt),
+                 ops.RelSpec(arena.ptr("x_ubs", t0), W, L.F_ubs, arena.ptr("ip_near", t0), W, T * L.cap_ubs)]
+        params = []
+        for c in convs:
+            params += [c.fc_src.weight, c.fc_src.bias, c.fc_dst.weight, c.fc_dst.bias, c.attn, c.res_fc.weight,
+                       c.res_fc.bias]
+        c0 = convs[0]
+        out = ops.SegmentEncode.apply(arena.buf, specs, arena.ptr("x_agent", t0), W, L.F_ag, T, L.N, c0._num_heads,
+                                      c0._out_feats, c0._negative_slope, ops.GAT_RESIDUAL | ops.GAT_RELU, *params)
+        return out.view(T, L.N, 2 * self._hidden_size)
+
+    def arena_dims(self, arena):
+        if not isinstance(self.enc, GraphObservationEncoder):
+            return None
+        return self.fused_dims(arena.layout.U)
+
+    def arena_sequence(self, arena, t0, T, h0):
+        """``forward_sequence`` over arena slots ``t0 .. t0+T-1`` (with autograd when enabled)."""
+        dims = self.arena_dims(arena)
+        if dims is None:
+            raise NotImplementedError("arena path needs the graph encoder and the fused step configuration")
+        params = self._fused_params()
+        packed = self._packed(dims, params)
+        xin = self._arena_xin(arena, t0, T)
+        mask = arena.sec("mask")[t0:t0 + T].contiguous() if dims.tarmac else None
+        h0 = h0.contiguous()
+        if th.is_grad_enabled() and any(p is not None and p.requires_grad for p in params.values()):
+            q, h_last, _ = ops.AgentSequence.apply(xin, h0, mask, dims, packed, *[params[k] for k in ops.PARAM_ORDER])
+            return q, h_last
+        q, h_all = ops.agent_seq_infer(dims, packed, xin, h0, mask)
+        return q, h_all[T - 1]
+
+    @th.no_grad()
+    def arena_step(self, arena, t, q_out=None):
+        """Inference on slot t: reads ``arena.h[t]``, writes ``arena.h[t+1]`` and the greedy actions ``arena.acts[t]``;
+        returns the Q values.  Three launches (two relations + the fused step), no allocation-dependent host logic,
+        so the call can be captured in a CUDA graph."""
+        dims = self.arena_dims(arena)
+        packed = self._packed(dims, self._fused_params())
+        xin = self._arena_xin(arena, t, 1)
+        mask = arena.sec("mask", t) if dims.tarmac else None
+        q, _, _ = ops.agent_seq_infer(dims, packed, xin, arena.h[t], mask, h_out=arena.h[t + 1].unsqueeze(0),
+                                      q=q_out, acts=arena.acts[t].unsqueeze(0))
+        return q[0]
+
     def forward(self, g, h):
         if not th.is_grad_enabled() and h.is_cuda:
             block, mask = self._talk_mask(g)

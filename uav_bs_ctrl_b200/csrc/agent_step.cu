@@ -129,21 +129,40 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ W, int ldw, 
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[c][r] = 0.f;
         if (active) {
+            // Weights stream from L2 (~250-cycle latency): register double buffering keeps KB 16-byte loads per
+            // thread in flight while the previous block of KB k-rows is consumed from registers.
+            constexpr int KB = 8;
             const int k0 = ks * kchunk, k1 = min(Kd, k0 + kchunk);
             const float* wp = W + 4 * ct;
             const float* ap = A + 4 * rt;
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
-                const float4 x = *reinterpret_cast<const float4*>(ap + k * RP);
-                acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
-                acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
-                acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
-                acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
-                acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
-                acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
-                acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
-                acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 wn[KB];
+#pragma unroll
+            for (int i = 0; i < KB; ++i)
+                wn[i] = (k0 + i < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)(k0 + i) * ldw)) : zero4;
+            for (int kb = k0; kb < k1; kb += KB) {
+                float4 wc[KB];
+#pragma unroll
+                for (int i = 0; i < KB; ++i) wc[i] = wn[i];
+#pragma unroll
+                for (int i = 0; i < KB; ++i) {
+                    const int k = kb + KB + i;
+                    wn[i] = (k < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw)) : zero4;
+                }
+#pragma unroll
+                for (int i = 0; i < KB; ++i) {
+                    const int k = min(kb + i, k1 - 1);          // rows past k1 carry zero weights
+                    const float4 w = wc[i];
+                    const float4 x = *reinterpret_cast<const float4*>(ap + k * RP);
+                    acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
+                    acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
+                    acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
+                    acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
+                    acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
+                    acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
+                    acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
+                    acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+                }
             }
         }
         if (ksplit > 1) {                                   // tiles*ksplit <= NT here: single pass of the base loop

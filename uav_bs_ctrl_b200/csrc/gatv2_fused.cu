@@ -30,6 +30,10 @@ struct GatArgs {
     const float* grad_out; const float* out_in; const float* smax_in; const float* ssum_in;
     float* partial; float* grad_x_src; float* grad_x_dst;
     int n_dst; int F_d; int D; float slope; int flags;
+    // strided segments (one per timestep of a sequence arena): destination v belongs to segment v / n_dst_seg whose
+    // x_src / x_dst / indptr / src_idx start seg * st_* elements after the base pointers (indptr is segment-local).
+    // Outputs are indexed by the global destination id with row strides ld_out / ld_gout.
+    int n_dst_seg; long long st_xsrc, st_xdst, st_ip, st_sidx; int ld_out, ld_gout;
 };
 
 template <int FS>
@@ -90,11 +94,17 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
         const bool active = v < a.n_dst;
         int beg = 0, end = 0;
         float xv0 = 0.f, xv1 = 0.f;
+        const int seg = active ? v / a.n_dst_seg : 0;
+        const int vl = v - seg * a.n_dst_seg;
+        const float* xsrc = a.x_src + seg * a.st_xsrc;
+        const int* sidx = a.src_idx ? a.src_idx + seg * a.st_sidx : nullptr;
         if (active) {
-            beg = __ldg(a.indptr + v);
-            end = __ldg(a.indptr + v + 1);
-            xv0 = __ldg(a.x_dst + (size_t)v * a.F_d);
-            xv1 = a.F_d > 1 ? __ldg(a.x_dst + (size_t)v * a.F_d + 1) : 0.f;
+            const int* ip = a.indptr + seg * a.st_ip;
+            const float* xd = a.x_dst + seg * a.st_xdst + (size_t)vl * a.F_d;
+            beg = __ldg(ip + vl);
+            end = __ldg(ip + vl + 1);
+            xv0 = __ldg(xd);
+            xv1 = a.F_d > 1 ? __ldg(xd + 1) : 0.f;
         }
         // destination part of the score pre-activation, shared by all edges of v
         for (int ch = li; ch < H; ch += GS) {
@@ -111,9 +121,9 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
             for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
         }
         for (int e = beg + li; e < end; e += GS) {
-            const size_t u = a.src_idx ? (size_t)__ldg(a.src_idx + e) : (size_t)e;
+            const size_t u = sidx ? (size_t)__ldg(sidx + e) : (size_t)e;
             float x[FS];
-            load_row<FS>(a.x_src, u, x);
+            load_row<FS>(xsrc, u, x);
 #pragma unroll
             for (int k = 0; k < HEADS; ++k) {
                 const float4* wk = wA + k * D;
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
                     }
                     if (has_res) o += fmaf(r.y, xv1, fmaf(r.x, xv0, r.z));
                     if (relu) o = fmaxf(o, 0.f);
-                    a.out[(size_t)v * H + ch] = o;
+                    a.out[(size_t)v * a.ld_out + ch] = o;
                 }
                 if (li == 0 && a.smax != nullptr) {
                     a.smax[(size_t)v * HEADS + k] = l[k] > 0.f ? m[k] : 0.f;
@@ -215,14 +225,19 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
 
     const int total_warps = gridDim.x * 4;
     for (int v = blockIdx.x * 4 + warp; v < a.n_dst; v += total_warps) {
-        const int beg = __ldg(a.indptr + v), end = __ldg(a.indptr + v + 1);
-        const float xv0 = __ldg(a.x_dst + (size_t)v * FD);
-        const float xv1 = FD > 1 ? __ldg(a.x_dst + (size_t)v * FD + 1) : 0.f;
+        const int seg = v / a.n_dst_seg, vl = v - seg * a.n_dst_seg;
+        const float* xsrc = a.x_src + seg * a.st_xsrc;
+        const int* sidx = a.src_idx ? a.src_idx + seg * a.st_sidx : nullptr;
+        const int* ip = a.indptr + seg * a.st_ip;
+        const float* xd = a.x_dst + seg * a.st_xdst + (size_t)vl * FD;
+        const int beg = __ldg(ip + vl), end = __ldg(ip + vl + 1);
+        const float xv0 = __ldg(xd);
+        const float xv1 = FD > 1 ? __ldg(xd + 1) : 0.f;
         float gp[CPL], ft[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            const size_t idx = (size_t)v * H + lane * CPL + j;
-            const float go = __ldg(a.grad_out + idx), oo = __ldg(a.out_in + idx);
+            const int chj = lane * CPL + j;
+            const float go = __ldg(a.grad_out + (size_t)v * a.ld_gout + chj), oo = __ldg(a.out_in + (size_t)v * a.ld_out + chj);
             gp[j] = (relu && !(oo > 0.f)) ? 0.f : go;
             const float res = has_res ? fmaf(wr[j][1], xv1, fmaf(wr[j][0], xv0, brr[j])) : 0.f;
             ft[j] = oo - res;                                   // only used where gp != 0
@@ -260,9 +275,9 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
                 const int cnt = min(32, end - e0);
                 int u_lane = 0;
                 if (lane < cnt) {
-                    u_lane = a.src_idx ? __ldg(a.src_idx + e0 + lane) : (e0 + lane);
+                    u_lane = sidx ? __ldg(sidx + e0 + lane) : (e0 + lane);
                     float xr[FS];
-                    load_row<FS>(a.x_src, (size_t)u_lane, xr);
+                    load_row<FS>(xsrc, (size_t)u_lane, xr);
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                     t.x = xr[0];
                     if constexpr (FS > 1) t.y = xr[1];
@@ -314,8 +329,9 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
                         for (int f = 0; f < FS; ++f) {
                             const float tot = warp_sum(gxs[f]);
                             if (lane == 0) {
-                                if (a.src_idx) atomicAdd(a.grad_x_src + (size_t)u * FS + f, tot);
-                                else a.grad_x_src[(size_t)u * FS + f] = tot;
+                                float* gx = a.grad_x_src + seg * a.st_xsrc + (size_t)u * FS + f;
+                                if (a.src_idx) atomicAdd(gx, tot);
+                                else *gx = tot;
                             }
                         }
                     }
@@ -341,8 +357,9 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
             }
             t0 = warp_sum(t0); t1 = warp_sum(t1);
             if (lane == 0) {
-                a.grad_x_dst[(size_t)v * FD] = t0;
-                if (FD > 1) a.grad_x_dst[(size_t)v * FD + 1] = t1;
+                float* gd = a.grad_x_dst + seg * a.st_xdst + (size_t)vl * FD;
+                gd[0] = t0;
+                if (FD > 1) gd[1] = t1;
             }
         }
     }
@@ -466,7 +483,23 @@ extern "C" UBS_API int ubs_gatv2_fwd(const float* x_src, const float* x_dst, con
                              const float* attn, const float* W_res, const float* b_res,
                              float* out, float* smax, float* ssum, int64_t n_dst, int64_t n_edges,
                              int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream) {
+    return ubs_gatv2_seg_fwd(x_src, x_dst, indptr, src_idx, W_src, b_src, W_dst, b_dst, attn, W_res, b_res, out, smax,
+                             ssum, 1, n_dst, n_edges, 0, 0, 0, 0, heads * D, F_s, F_d, heads, D, negative_slope, flags,
+                             stream);
+}
+
+extern "C" UBS_API int ubs_gatv2_seg_fwd(const float* x_src, const float* x_dst, const int32_t* indptr,
+                                 const int32_t* src_idx, const float* W_src, const float* b_src, const float* W_dst,
+                                 const float* b_dst, const float* attn, const float* W_res, const float* b_res,
+                                 float* out, float* smax, float* ssum, int64_t n_seg, int64_t n_dst_seg,
+                                 int64_t n_edges, int64_t st_xsrc, int64_t st_xdst, int64_t st_ip, int64_t st_sidx,
+                                 int64_t ld_out, int F_s, int F_d, int heads, int D, float negative_slope, int flags,
+                                 void* stream) {
+    const int64_t n_dst = n_seg * n_dst_seg;
     if (int rc = ubs::check_shape("ubs_gatv2_fwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(n_seg >= 1 && n_dst_seg >= 0 && ld_out >= heads * D, "ubs_gatv2_fwd: bad segment description");
+    UBS_REQUIRE(F_s != 4 || st_xsrc % 4 == 0, "ubs_gatv2_fwd: segment stride breaks 16-byte row alignment");
+    UBS_REQUIRE(F_s != 2 || st_xsrc % 2 == 0, "ubs_gatv2_fwd: segment stride breaks 8-byte row alignment");
     UBS_REQUIRE(n_dst >= 0 && n_dst < (1ll << 31) && n_edges >= 0 && n_edges < (1ll << 31), "ubs_gatv2_fwd: sizes out of range");
     UBS_REQUIRE((smax == nullptr) == (ssum == nullptr), "ubs_gatv2_fwd: smax and ssum must both be given or both NULL");
     UBS_REQUIRE(!(flags & UBS_GAT_RESIDUAL) || W_res != nullptr, "ubs_gatv2_fwd: residual flag without W_res");
@@ -477,6 +510,8 @@ extern "C" UBS_API int ubs_gatv2_fwd(const float* x_src, const float* x_dst, con
     a.W_src = W_src; a.b_src = b_src; a.W_dst = W_dst; a.b_dst = b_dst; a.attn = attn; a.W_res = W_res; a.b_res = b_res;
     a.out = out; a.smax = smax; a.ssum = ssum;
     a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
+    a.n_dst_seg = (int)(n_dst_seg > 0 ? n_dst_seg : 1); a.st_xsrc = st_xsrc; a.st_xdst = st_xdst; a.st_ip = st_ip;
+    a.st_sidx = st_sidx; a.ld_out = (int)ld_out; a.ld_gout = (int)ld_out;
     int rc = 0;
     UBS_DISPATCH_FS_HEADS(ubs::launch_fwd, a, n_edges, (cudaStream_t)stream)
     return rc;
@@ -494,7 +529,24 @@ extern "C" UBS_API int ubs_gatv2_bwd(const float* x_src, const float* x_dst, con
                              int64_t n_dst, int64_t n_edges, int64_t n_src, int F_s, int F_d, int heads, int D,
                              float negative_slope, int flags, void* stream) {
     (void)n_src;
+    return ubs_gatv2_seg_bwd(x_src, x_dst, indptr, src_idx, W_src, b_src, W_dst, b_dst, attn, W_res, b_res, out,
+                             grad_out, smax, ssum, grad_params, grad_x_src, grad_x_dst, workspace, 1, n_dst, n_edges,
+                             0, 0, 0, 0, heads * D, heads * D, F_s, F_d, heads, D, negative_slope, flags, stream);
+}
+
+extern "C" UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst, const int32_t* indptr,
+                                 const int32_t* src_idx, const float* W_src, const float* b_src, const float* W_dst,
+                                 const float* b_dst, const float* attn, const float* W_res, const float* b_res,
+                                 const float* out, const float* grad_out, const float* smax, const float* ssum,
+                                 float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                                 int64_t n_seg, int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst,
+                                 int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout, int F_s, int F_d,
+                                 int heads, int D, float negative_slope, int flags, void* stream) {
+    const int64_t n_dst = n_seg * n_dst_seg;
     if (int rc = ubs::check_shape("ubs_gatv2_bwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(n_seg >= 1 && n_dst_seg >= 0 && ld_out >= heads * D && ld_gout >= heads * D, "ubs_gatv2_bwd: bad segment description");
+    UBS_REQUIRE(F_s != 4 || st_xsrc % 4 == 0, "ubs_gatv2_bwd: segment stride breaks 16-byte row alignment");
+    UBS_REQUIRE(F_s != 2 || st_xsrc % 2 == 0, "ubs_gatv2_bwd: segment stride breaks 8-byte row alignment");
     UBS_REQUIRE(n_dst >= 0 && n_dst < (1ll << 31) && n_edges >= 0 && n_edges < (1ll << 31), "ubs_gatv2_bwd: sizes out of range");
     UBS_REQUIRE(smax && ssum && out && grad_out && grad_params && workspace, "ubs_gatv2_bwd: NULL argument");
     UBS_REQUIRE(((uintptr_t)x_src % (F_s == 4 ? 16 : F_s == 2 ? 8 : 4)) == 0, "ubs_gatv2_bwd: x_src misaligned");
@@ -512,6 +564,8 @@ extern "C" UBS_API int ubs_gatv2_bwd(const float* x_src, const float* x_dst, con
     a.grad_out = grad_out; a.out_in = out; a.smax_in = smax; a.ssum_in = ssum;
     a.partial = workspace; a.grad_x_src = grad_x_src; a.grad_x_dst = grad_x_dst;
     a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
+    a.n_dst_seg = (int)(n_dst_seg > 0 ? n_dst_seg : 1); a.st_xsrc = st_xsrc; a.st_xdst = st_xdst; a.st_ip = st_ip;
+    a.st_sidx = st_sidx; a.ld_out = (int)ld_out; a.ld_gout = (int)ld_gout;
     int rc = 0;
     UBS_DISPATCH_FS_HEADS(ubs::launch_bwd, a, H, st)
     if (rc) return rc;

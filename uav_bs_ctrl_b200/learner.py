@@ -167,8 +167,12 @@ class MultiAgentQLearner:
         return th.stack(agent_out), th.stack(target_out)
 
     def compute_loss(self, obs, h, h_targ, acts, rews, dones):
-        T = self.max_seq_len
         agent_out, target_out = self._unroll(obs, h, h_targ)
+        return self._td_loss(agent_out, target_out, acts, rews, dones)
+
+    def _td_loss(self, agent_out, target_out, acts, rews, dones):
+        """Reference ``learner.py:134-154`` (no mixer): ``agent_out (T+1,N,A)``, ``target_out (T,N,A)``."""
+        T = target_out.shape[0]
         qvals = agent_out[:-1].gather(2, acts)
         if not self.double_q:
             next_vals = target_out.max(2, keepdim=True)[0]
@@ -208,12 +212,15 @@ class MultiAgentQLearner:
             samples = self.buffer.sample(self.batch_size)
         obs, h, h_targ, acts, rews, dones = self.gather_batch(samples)
         loss, qvals = self.compute_loss(obs, h, h_targ, acts, rews, dones)
+        return self._optimise(loss, qvals, sync)
 
+    def _optimise(self, loss, qvals, sync):
+        """Reference ``learner.py:157-173``: backward, (DP all-reduce,) value clip, AdamW, polyak target."""
         self.grad_bucket.zero_()
         loss.backward()
         self.grad_bucket.rebind()
         dist.avg_grads(self.grad_bucket)                                     # DP: one flat all-reduce
-        nn.utils.clip_grad_value_(self.policy_net.parameters(), clip_value=1)
+        self.grad_bucket.flat.clamp_(-1.0, 1.0)                              # == clip_grad_value_(params, 1), one launch
         self.optimizer.step()
         with th.no_grad():
             pp, tp = list(self.policy_net.parameters()), list(self.target_net.parameters())
@@ -222,6 +229,84 @@ class MultiAgentQLearner:
         if sync:
             return dict(LossQ=loss.item(), QVals=qvals.detach().cpu().numpy())
         return dict(LossQ=loss.detach(), QVals=qvals.detach())
+
+    # ------------------------------------------------------------------------------------------ sequence-arena path
+    def new_arena(self, n_gts, n_slots=None):
+        """Device-resident replay entry: ``max_seq_len + 1`` observation packets + hidden states + actions."""
+        from .arena import PacketLayout, SequenceArena
+        fg = self.obs_shape["gt"] if isinstance(self.obs_shape, dict) else 4
+        L = PacketLayout(self.n_envs, self.n_agents, n_gts, F_ag=self.obs_shape["agent"], F_gt=fg,
+                         F_ubs=self.obs_shape["ubs"])
+        return SequenceArena(L, n_slots or self.max_seq_len + 1, self.args.hidden_size, self.device)
+
+    def begin_sequence(self, arena, h0=None):
+        """Start of a T-step window on ``arena``: initial hidden state and the window's exploration noise."""
+        if h0 is None:
+            arena.h[0].zero_()                       # init_hidden() is zeros (reference gnn_agents.py:48-49)
+        else:
+            arena.h[0].copy_(h0)
+        if not hasattr(arena, "explore_u"):          # fixed addresses: captured act graphs read these buffers
+            arena.explore_u = th.empty(arena.S, self.n_envs, device=self.device)
+            arena.explore_a = th.empty(arena.S, arena.layout.N, dtype=th.int64, device=self.device)
+        arena.explore_u.uniform_()
+        arena.explore_a.random_(0, self.n_actions)
+
+    def _act_arena_eager(self, arena, t):
+        q = self.policy_net.arena_step(arena, t)
+        explore = (arena.explore_u[t] <= self._eps_dev).repeat_interleave(self.n_agents)
+        arena.acts[t].copy_(th.where(explore, arena.explore_a[t], arena.acts[t]))
+        return q
+
+    def act_arena(self, arena, t, eps_thres):
+        """``act`` on arena slot t (observation already staged with ``arena.load``): writes ``arena.h[t+1]`` and the
+        ε-greedy actions ``arena.acts[t]`` (returned, on the device).  With ``args.cuda_graphs`` the three kernels and
+        the ε-greedy ops of every slot are captured once and replayed."""
+        if not hasattr(self, "_eps_dev"):
+            self._eps_dev = th.zeros((), device=self.device)
+            self._eps_host, self._act_graphs = None, {}
+        if self._eps_host != eps_thres:
+            self._eps_dev.fill_(float(eps_thres))
+            self._eps_host = eps_thres
+        if not getattr(self.args, "cuda_graphs", False):
+            self._act_arena_eager(arena, t)
+            return arena.acts[t]
+        key = (id(arena), t)
+        g = self._act_graphs.get(key)
+        if g is None:
+            # parameters must already be packed: the pack kernel must not be part of the captured graph
+            self.policy_net._packed(self.policy_net.arena_dims(arena), self.policy_net._fused_params())
+            side = th.cuda.Stream()
+            side.wait_stream(th.cuda.current_stream())
+            with th.cuda.stream(side):
+                self._act_arena_eager(arena, t)          # warm-up outside capture
+            th.cuda.current_stream().wait_stream(side)
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._act_arena_eager(arena, t)
+            self._act_graphs[key] = g
+        g.replay()
+        return arena.acts[t]
+
+    def update_arena(self, arena, sync=True):
+        """One BPTT update on the window held by ``arena`` (same math as ``update``; no graph objects, no re-batching):
+        one strided-segment encoder launch per relation over all T+1 timesteps and one persistent recurrent kernel,
+        for the policy (with grad) and for the target network."""
+        T = self.max_seq_len
+        acts = arena.acts[:T].unsqueeze(-1)
+        rews, dones = arena.rewards(T), arena.dones(T)
+        if self.args.share_reward:
+            rews = rews.mean(2, keepdim=True)
+        keep = (1 - arena.sec("done", 1)).repeat_interleave(self.n_agents).unsqueeze(1)     # next_h = (1 - done) * next_h
+        h0, h_targ = arena.h[0], arena.h[1] * keep
+        agent_out, _ = self.policy_net.arena_sequence(arena, 0, T + 1, h0)
+        with th.no_grad():
+            target_out, _ = self.target_net.arena_sequence(arena, 1, T, h_targ)
+        loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones)
+        out = self._optimise(loss, qvals, sync)
+        # refresh the packed weights outside any captured graph (AdamW / polyak updated the parameters in place)
+        for net in (self.policy_net, self.target_net):
+            net._packed(net.arena_dims(arena), net._fused_params())
+        return out
 
     # ------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, path, stamp):

@@ -258,15 +258,23 @@ def agent_pack(dims: AgentDims, params: dict, out=None):
     return out
 
 
-def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False):
-    """Inference: ``xin (T,N,Fin)``, ``h0 (N,H)`` -> ``q (T,N,A)``, ``h_out (T,N,H)`` [, greedy actions (T,N) int64]."""
+def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False, h_out=None, q=None, acts=None):
+    """Inference: ``xin (T,N,Fin)``, ``h0 (N,H)`` -> ``q (T,N,A)``, ``h_out (T,N,H)`` [, greedy actions (T,N) int64].
+    ``h_out`` / ``q`` / ``acts`` may be preallocated contiguous destinations (e.g. slices of a sequence arena)."""
     lib = _lib.load()
     _lib.require_cuda(xin, h0, packed)
     xin, h0 = _f32c(xin), _f32c(h0)
     T, N = xin.shape[0], xin.shape[1]
-    h_out = th.empty(T, N, dims.H, dtype=th.float32, device=xin.device)
-    q = th.empty(T, N, dims.A, dtype=th.float32, device=xin.device)
-    acts = th.empty(T, N, dtype=th.int64, device=xin.device) if want_actions else None
+    if h_out is None:
+        h_out = th.empty(T, N, dims.H, dtype=th.float32, device=xin.device)
+    if q is None:
+        q = th.empty(T, N, dims.A, dtype=th.float32, device=xin.device)
+    if acts is None and want_actions:
+        acts = th.empty(T, N, dtype=th.int64, device=xin.device)
+    for t_, n_ in ((h_out, T * N * dims.H), (q, T * N * dims.A), (acts, T * N)):
+        if t_ is not None and (not t_.is_contiguous() or t_.numel() != n_):
+            raise ValueError("agent_seq_infer: output buffers must be contiguous and exactly sized")
+    want_actions = acts is not None
     with _timed("agent_seq_fwd", (T, N, dims.ints(), False)):
         _lib.check(lib.ubs_agent_seq_fwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(xin), _lib.ptr(h0), _lib.ptr(mask),
                                          _lib.ptr(h_out), _lib.ptr(q), _lib.ptr(acts), None, None, None, None,
@@ -348,3 +356,78 @@ class AgentSequence(th.autograd.Function):
             g["W_aggr"], g["b_aggr"] = dp.t() @ xin.view(TN, dims.Fin), dp.sum(0)
         grads = tuple(g.get(k) if has else None for k, has in zip(PARAM_ORDER, ctx.has))
         return (d_xin if ctx.needs_input_grad[0] else None, d_h0, None, None, None) + grads
+
+
+# ====================================================================================================================
+# Strided-segment relation encoder (ubs_gatv2_seg_fwd / ubs_gatv2_seg_bwd): all timesteps of an arena in one launch per
+# relation, every relation writing its own column block of ONE (rows, R*H) output buffer.
+class RelSpec:
+    """One relation of a strided-segment encode: raw device addresses + strides (elements) + feature widths."""
+
+    def __init__(self, x_src_ptr, st_xsrc, F_s, indptr_ptr, st_ip, n_edges_hint, src_idx_ptr=None, st_sidx=0):
+        self.x_src_ptr, self.st_xsrc, self.F_s = x_src_ptr, st_xsrc, F_s
+        self.indptr_ptr, self.st_ip, self.n_edges_hint = indptr_ptr, st_ip, n_edges_hint
+        self.src_idx_ptr, self.st_sidx = src_idx_ptr, st_sidx
+
+
+class SegmentEncode(th.autograd.Function):
+    """``forward(keepalive, specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, slope, flags, *params)``
+    with ``params`` = 7 tensors per relation ``(W_src, b_src, W_dst, b_dst, attn, W_res, b_res)``.
+    Returns ``(n_seg * n_dst_seg, len(specs) * H)``.  Observations are leaves: only parameter gradients are produced.
+    ``keepalive`` is the tensor that owns the addressed memory (the arena buffer)."""
+
+    @staticmethod
+    def forward(ctx, keepalive, specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, slope, flags, *params):
+        lib = _lib.load()
+        dev = keepalive.device
+        H, R = heads * D, len(specs)
+        rows = n_seg * n_dst_seg
+        need_grad = any(p is not None and p.requires_grad for p in params)
+        out = th.empty(rows, R * H, dtype=th.float32, device=dev)
+        stats = th.empty(R, 2, rows, heads, dtype=th.float32, device=dev) if need_grad else None
+        ps = [_f32c(p.detach()) if p is not None else None for p in params]
+        for r, sp in enumerate(specs):
+            W = ps[7 * r:7 * r + 7]
+            with _timed("gatv2_fwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, need_grad)):
+                _lib.check(lib.ubs_gatv2_seg_fwd(
+                    sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
+                    out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]) if need_grad else None,
+                    _lib.ptr(stats[r, 1]) if need_grad else None, n_seg, n_dst_seg, sp.n_edges_hint, sp.st_xsrc, st_xdst,
+                    sp.st_ip, sp.st_sidx, R * H, sp.F_s, F_d, heads, D, float(slope), int(flags), _lib.stream()),
+                    "ubs_gatv2_seg_fwd")
+        if need_grad:
+            ctx.save_for_backward(keepalive, out, stats, *[p for p in ps if p is not None])
+            ctx.cfg = (specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, float(slope), int(flags),
+                       [p is not None for p in params], [None if p is None else tuple(p.shape) for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        keepalive, out, stats, *saved = ctx.saved_tensors
+        specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, slope, flags, has, shapes = ctx.cfg
+        lib = _lib.load()
+        dev = out.device
+        H, R = heads * D, len(specs)
+        rows = n_seg * n_dst_seg
+        grad_out = _f32c(grad_out)
+        it = iter(saved)
+        ps = [next(it) if h else None for h in has]
+        grads = []
+        for r, sp in enumerate(specs):
+            W = ps[7 * r:7 * r + 7]
+            Pn = H * (sp.F_s + 2 * F_d + 4)
+            gparams = th.empty(Pn, dtype=th.float32, device=dev)
+            ws = th.empty(int(lib.ubs_gatv2_bwd_workspace(rows, sp.F_s, F_d, heads, D)), dtype=th.float32, device=dev)
+            with _timed("gatv2_bwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, True)):
+                _lib.check(lib.ubs_gatv2_seg_bwd(
+                    sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
+                    out.data_ptr() + 4 * r * H, grad_out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]),
+                    _lib.ptr(stats[r, 1]), _lib.ptr(gparams), None, None, _lib.ptr(ws), n_seg, n_dst_seg,
+                    sp.n_edges_hint, sp.st_xsrc, st_xdst, sp.st_ip, sp.st_sidx, R * H, R * H, sp.F_s, F_d, heads, D,
+                    slope, flags, _lib.stream()), "ubs_gatv2_seg_bwd")
+            o = 0
+            for n, idx in ((H * sp.F_s, 0), (H, 1), (H * F_d, 2), (H, 3), (H, 4), (H * F_d, 5), (H, 6)):
+                k = 7 * r + idx
+                grads.append(gparams[o:o + n].view(shapes[k]) if has[k] else None)
+                o += n
+        return (None,) * 11 + tuple(grads)

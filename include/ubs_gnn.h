@@ -46,6 +46,9 @@ UBS_API const char* ubs_last_error(void);
 /* Number of kernel launches issued through this library by the calling process (bench "gpu_launches"). */
 UBS_API int64_t ubs_launch_count(void);
 UBS_API void ubs_reset_launch_count(void);
+/* Replaying a captured CUDA graph re-launches kernels without passing through this library: the host code that
+ * replays a graph adds the number of library kernels the graph contains.                                        */
+UBS_API void ubs_add_launch_count(int64_t n);
 
 /* ---- GATv2 relation, fused projection (F_s <= 4, F_d <= 2, H = heads*D in {32,64,128}) -----------------
  * out[v, k, :] = act( sum_e alpha[e,k] * (W_src x_src[u_e] + b_src)[k,:] + W_res x_dst[v] + b_res )
@@ -153,6 +156,27 @@ UBS_API int ubs_agent_seq_bwd(int H, int M, int K, int A, int U, int Fin, int fl
                       const float* sv_alpha, const float* sv_gate, const float* dq, const float* dh_last,
                       float* d_xin, float* d_h0, float* st_dgi, float* st_dgh, float* st_dvsq, float* st_dpre,
                       int64_t n_rows, int n_steps, void* stream);
+
+/* ---- Sequence path with recurrent weights resident in shared memory ----------------------------------------------
+ * Same math as ubs_agent_seq_*, split along the one true dependency of a BPTT window.  The caller computes, for all
+ * n_steps*n_rows rows at once (batched GEMMs; the encoder does not depend on h, gnn_agents.py:53):
+ *     x = relu(W_aggr xin + b_aggr),  pv = W_vsq[:, :H] x + b_vsq  (n_steps,n_rows,round4(M+2K)),
+ *     pg = W_ih[:, :H] x + b_ih  (n_steps,n_rows,3H)
+ * and afterwards the Q head, the x-path gradients and every parameter gradient.  The kernel keeps
+ *     wt_vsq_h = W_vsq[:, H:]^T (H, round4(M+2K)), wt_ih_c = W_ih[:, H:]^T (M, 3H), wt_hh = W_hh^T (H, 3H), b_hh
+ * in shared memory for the whole sequence (backward: w_hh (3H,H) and w_ih_c = W_ih[:, H:] (3H,M), original layouts).
+ * Returns 3 when the weights do not fit (ubs_agent_seq2_smem_bytes > 227 KB): use ubs_agent_seq_* then.            */
+UBS_API int64_t ubs_agent_seq2_smem_bytes(int H, int M, int K, int U, int flags, int backward);
+UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags, const float* wt_vsq_h, const float* wt_ih_c,
+                       const float* wt_hh, const float* b_hh, const float* pv, const float* pg, const float* h0,
+                       const uint32_t* mask, float* h_out, float* sv_vsq, float* sv_alpha, float* sv_c,
+                       float* sv_gate, int64_t n_rows, int n_steps, void* stream);
+/* dhq (n_steps,n_rows,H) = dq W_out (+ grad of the last hidden state on the last step).  Outputs the stashes
+ * st_dgi / st_dgh (.., 3H), st_dvsq (.., round4(M+2K)) and d_h0 (nullable).                                      */
+UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags, const float* w_hh, const float* w_ih_c,
+                       const float* h0, const float* h_out, const float* sv_vsq, const float* sv_alpha,
+                       const float* sv_gate, const float* dhq, float* st_dgi, float* st_dgh, float* st_dvsq,
+                       float* d_h0, int64_t n_rows, int n_steps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ _PROTOS = {
     "ubs_last_error": (C.c_char_p, []),
     "ubs_launch_count": (_i64, []),
     "ubs_reset_launch_count": (None, []),
+    "ubs_add_launch_count": (None, [_i64]),
     "ubs_gatv2_fwd": (C.c_int, [_F, _F, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i64,
                                 _int, _int, _int, _int, _flt, _int, _ptr]),
     "ubs_gatv2_bwd_workspace": (_i64, [_i64, _int, _int, _int, _int]),
@@ -35,6 +36,9 @@ _PROTOS = {
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),
     "ubs_gatv2_seg_bwd": (C.c_int, [_F] * 19 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
+    "ubs_agent_seq2_smem_bytes": (_i64, [_int] * 6),
+    "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _int, _ptr]),
+    "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _int, _ptr]),
     "ubs_agent_pack_size": (_i64, [_int] * 7),
     "ubs_agent_pack": (C.c_int, [_int] * 7 + [_F] * 15 + [_ptr]),
     "ubs_agent_seq_fwd": (C.c_int, [_int] * 7 + [_F] * 11 + [_i64, _int, _ptr]),
@@ -94,6 +98,10 @@ def launch_count() -> int:
 
 def reset_launch_count():
     load().ubs_reset_launch_count()
+
+
+def add_launches(n: int):
+    load().ubs_add_launch_count(int(n))
 
 
 def require_cuda(*tensors):

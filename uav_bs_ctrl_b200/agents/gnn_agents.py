@@ -300,6 +300,7 @@ class GnnAgent(nn.Module):
         self._msg_size, self._key_size = getattr(args, "msg_size", 0), getattr(args, "key_size", 0)
         self._n_rounds = getattr(args, "n_rounds", 1)
         self._pack_cache = {}
+        self.use_seq2 = True          # resident-weight sequence kernels when they fit (False: weight-streaming kernels)
 
     def init_hidden(self):
         return th.zeros(1, self._hidden_size)
@@ -375,13 +376,24 @@ class GnnAgent(nn.Module):
         dims = self.fused_dims(block)
         if dims is None:
             raise NotImplementedError("forward_sequence needs the fused configuration (c in {None,'tarmac'}, Linear head)")
-        params = self._fused_params()
-        packed = self._packed(dims, params)
         xin = self._encode_pre(gb).view(T, N, dims.Fin)
-        h0 = h0.contiguous()
-        if th.is_grad_enabled() and (xin.requires_grad or any(p is not None and p.requires_grad for p in params.values())):
-            q, h_last, _ = ops.AgentSequence.apply(xin, h0, None if mask is None else mask.view(T, N), dims, packed,
-                                                   *[params[k] for k in ops.PARAM_ORDER])
+        return self._run_sequence(dims, xin, h0.contiguous(), None if mask is None else mask.view(T, N))
+
+    def _run_sequence(self, dims, xin, h0, mask):
+        """Recurrent part of a whole window.  Resident-weight kernels (``ubs_agent_seq2_*``) when the recurrent
+        weights fit shared memory (H = 64 configs), else the weight-streaming kernels (``ubs_agent_seq_*``)."""
+        params = self._fused_params()
+        T = xin.shape[0]
+        grad = th.is_grad_enabled() and (xin.requires_grad or any(p is not None and p.requires_grad for p in params.values()))
+        if self.use_seq2 and ops.seq2_supported(dims):
+            if grad:
+                q, h_last, _ = ops.AgentSequence2.apply(xin, h0, mask, dims, *[params[k] for k in ops.PARAM_ORDER])
+                return q, h_last
+            q, h_all = ops.agent_seq2_infer(dims, params, xin, h0, mask)
+            return q, h_all[T - 1]
+        packed = self._packed(dims, params)
+        if grad:
+            q, h_last, _ = ops.AgentSequence.apply(xin, h0, mask, dims, packed, *[params[k] for k in ops.PARAM_ORDER])
             return q, h_last
         q, h_all = ops.agent_seq_infer(dims, packed, xin, h0, mask)
         return q, h_all[T - 1]
@@ -412,16 +424,9 @@ class GnnAgent(nn.Module):
         dims = self.arena_dims(arena)
         if dims is None:
             raise NotImplementedError("arena path needs the graph encoder and the fused step configuration")
-        params = self._fused_params()
-        packed = self._packed(dims, params)
         xin = self._arena_xin(arena, t0, T)
         mask = arena.sec("mask")[t0:t0 + T].contiguous() if dims.tarmac else None
-        h0 = h0.contiguous()
-        if th.is_grad_enabled() and any(p is not None and p.requires_grad for p in params.values()):
-            q, h_last, _ = ops.AgentSequence.apply(xin, h0, mask, dims, packed, *[params[k] for k in ops.PARAM_ORDER])
-            return q, h_last
-        q, h_all = ops.agent_seq_infer(dims, packed, xin, h0, mask)
-        return q, h_all[T - 1]
+        return self._run_sequence(dims, xin, h0.contiguous(), mask)
 
     @th.no_grad()
     def arena_step(self, arena, t, q_out=None):

@@ -1,0 +1,440 @@
+// Persistent recurrent sequence kernels with the recurrent weights RESIDENT IN SHARED MEMORY (forward + backward).
+//
+// Same math as agent_step.cu (reference TarMAC.forward + GRUCell, algos/madrqn/agents/gnn_agents.py:248-271), but
+// split along the only true dependency of the BPTT window: everything that depends on the observation alone
+//     x  = relu(W_aggr [x_gt ‖ x_ubs] + b)         pv = W_vsq[:, :H] x + b_vsq         pg = W_ih[:, :H] x + b_ih
+// is computed for ALL T·N rows by batched library GEMMs before this kernel (the encoder does not depend on h,
+// gnn_agents.py:53), and the Q head / every x-path gradient / every parameter gradient after it.  What is left in the
+// time loop is the part that really is sequential,
+//     vsq = pv + W_vsq[:, H:] h        attention over the env block        gi = pg + W_ih[:, H:] c
+//     gh  = W_hh h + b_hh              GRU gates -> h'
+// 30.7 k of the 57.9 k MACs per agent row, whose weights (123 KB at H = M = 64, K = 16) stay in shared memory for the
+// whole sequence: no per-step weight traffic at all, and the hidden state never leaves the SM.
+// A CTA owns a tile of <= 16 agent rows (whole envs; envs never exchange data) for all timesteps.
+#include "common.cuh"
+#include "../../include/ubs_gnn.h"
+
+namespace ubs {
+namespace seq2 {
+
+constexpr int R = 16, RP = 20, NT = 256;
+
+struct Dims {
+    int H, M, K, U, flags;
+    __host__ __device__ bool tarmac() const { return flags & UBS_STEP_TARMAC; }
+    __host__ __device__ int V() const { return M + 2 * K; }
+    __host__ __device__ int Vp() const { return (V() + 3) & ~3; }
+    __host__ __device__ int rows_per_tile() const { return tarmac() ? (R / U) * U : R; }
+};
+
+// out[j*RP + r] = init + sum_{k<Kd} W[k*ldw + j] * A[k*RP + r],  W and A in SHARED memory (feature-major / K-major).
+// init: row-major GLOBAL tile g_init[(row0 + r) * ld_init + j] (pv / pg; prefetched into registers before the k loop)
+// and/or a per-column bias.  mode 0 store, 2 accumulate into out.  Thread tile 4 columns x 4 rows; split-K fills
+// the CTA for narrow outputs.  All threads call; ends with __syncthreads().
+__device__ __forceinline__ void gemm_s(const float* W, int ldw, const float* A, int Kd, float* out, int Nout,
+                                       const float* __restrict__ g_init, int64_t row0, int n_valid, int64_t ld_init,
+                                       const float* bias, int mode, float* scratch) {
+    const int ntc = Nout >> 2, tiles = ntc * 4;
+    int ksplit = 1;
+    while (ksplit < 8 && tiles * ksplit * 2 <= NT && Kd >= ksplit * 16) ksplit *= 2;
+    const int kchunk = (((Kd + ksplit - 1) / ksplit) + 3) & ~3;
+    for (int base = 0; base < tiles * ksplit; base += NT) {
+        const int t = base + threadIdx.x;
+        const bool active = t < tiles * ksplit;
+        const int ks = active ? t / tiles : 0, tile = active ? t - ks * tiles : 0;
+        const int ct = tile % ntc, rt = tile / ntc;
+        float acc[4][4];                                  // [row][col]
+        float4 ini[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ini[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && ks == 0 && g_init != nullptr) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (4 * rt + r < n_valid)
+                    ini[r] = __ldg(reinterpret_cast<const float4*>(g_init + (row0 + 4 * rt + r) * ld_init + 4 * ct));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        if (active) {
+            const int k0 = ks * kchunk, k1 = min(Kd, k0 + kchunk);
+            const float* wp = W + 4 * ct;
+            const float* ap = A + 4 * rt;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+                const float4 x = *reinterpret_cast<const float4*>(ap + k * RP);
+                acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
+                acc[0][2] = fmaf(x.x, w.z, acc[0][2]); acc[0][3] = fmaf(x.x, w.w, acc[0][3]);
+                acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
+                acc[1][2] = fmaf(x.y, w.z, acc[1][2]); acc[1][3] = fmaf(x.y, w.w, acc[1][3]);
+                acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
+                acc[2][2] = fmaf(x.z, w.z, acc[2][2]); acc[2][3] = fmaf(x.z, w.w, acc[2][3]);
+                acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
+                acc[3][2] = fmaf(x.w, w.z, acc[3][2]); acc[3][3] = fmaf(x.w, w.w, acc[3][3]);
+            }
+        }
+        if (ksplit > 1) {
+            if (active && ks > 0) {
+                float4* sp = reinterpret_cast<float4*>(scratch + ((ks - 1) * tiles + tile) * 16);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sp[r] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            }
+            __syncthreads();
+            if (active && ks == 0) {
+                for (int s = 1; s < ksplit; ++s) {
+                    const float4* sp = reinterpret_cast<const float4*>(scratch + ((s - 1) * tiles + tile) * 16);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 v = sp[r];
+                        acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
+                    }
+                }
+            }
+        }
+        if (active && ks == 0) {
+            const float ic[4][4] = {{ini[0].x, ini[0].y, ini[0].z, ini[0].w}, {ini[1].x, ini[1].y, ini[1].z, ini[1].w},
+                                    {ini[2].x, ini[2].y, ini[2].z, ini[2].w}, {ini[3].x, ini[3].y, ini[3].z, ini[3].w}};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 4 * ct + c;
+                const float b = bias ? bias[j] : 0.f;
+                float4* op = reinterpret_cast<float4*>(out + j * RP + 4 * rt);
+                float4 v = make_float4(acc[0][c] + ic[0][c] + b, acc[1][c] + ic[1][c] + b, acc[2][c] + ic[2][c] + b,
+                                       acc[3][c] + ic[3][c] + b);
+                if (mode == 2) { const float4 o = *op; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *op = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_tile(const float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, float* s) {
+    for (int i = threadIdx.x; i < R * F; i += NT) {
+        const int r = i / F, f = i - r * F;
+        s[f * RP + r] = r < n_valid ? __ldg(g + (row0 + r) * ld + f) : 0.f;
+    }
+}
+__device__ __forceinline__ void store_tile(float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, const float* s) {
+    for (int i = threadIdx.x; i < R * F; i += NT) {
+        const int r = i / F, f = i - r * F;
+        if (r < n_valid) g[(row0 + r) * ld + f] = s[f * RP + r];
+    }
+}
+__device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x * 4; i < n; i += NT * 4)
+        *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+}
+
+struct Args {
+    Dims d;
+    // resident weights, K-major: forward  wt_vsq_h [H][Vp], wt_ih_c [M][3H], wt_hh [H][3H], b_hh [3H]
+    //                            backward w_hh [3H][H], w_ih_c [3H][M]
+    const float *w0, *w1, *w2, *b_hh;
+    const float* pv; const float* pg; const float* h0; const uint32_t* mask;
+    float* h_out; float* sv_vsq; float* sv_alpha; float* sv_c; float* sv_gate;
+    // backward
+    const float* dhq; float* st_dgi; float* st_dgh; float* st_dvsq; float* d_h0;
+    int64_t N; int T;
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(NT) seq2_fwd_kernel(const Args a) {
+    extern __shared__ __align__(16) float sm[];
+    const Dims d = a.d;
+    const int H = d.H, H3 = 3 * H, M = d.M, K = d.K, U = d.U, Vp = d.Vp();
+    const bool tm = d.tarmac();
+    int o = 0;
+    auto take = [&](int n) { float* p = sm + o; o += (n + 3) & ~3; return p; };
+    float* wVH = take(tm ? H * Vp : 0);
+    float* wIC = take(tm ? M * H3 : 0);
+    float* wHH = take(H * H3);
+    float* bHH = take(H3);
+    float* sH = take(H * RP);
+    float* sVSQ = take(tm ? Vp * RP : 0);
+    float* sC = take(tm ? M * RP : 0);
+    float* sGI = take(H3 * RP);
+    float* sGH = take(H3 * RP);
+    float* sAl = take(tm ? U * RP : 0);
+    float* scratch = take(NT * 16);
+    if (tm) { copy_to_smem(wVH, a.w0, H * Vp); copy_to_smem(wIC, a.w1, M * H3); }
+    copy_to_smem(wHH, a.w2, H * H3);
+    copy_to_smem(bHH, a.b_hh, H3);
+
+    const int rpt = d.rows_per_tile();
+    const int64_t row0 = (int64_t)blockIdx.x * rpt;
+    const int n_valid = (int)min((int64_t)rpt, a.N - row0);
+    const int64_t n = a.N;
+    const bool training = a.sv_gate != nullptr;
+    const float scale = tm ? 1.0f / (float)K : 0.f;
+    load_tile(a.h0, row0, n_valid, H, H, sH);
+    __syncthreads();
+
+    for (int t = 0; t < a.T; ++t) {
+        const float* pg = a.pg + (size_t)t * n * H3;
+        if (tm) {
+            gemm_s(wVH, Vp, sH, H, sVSQ, Vp, a.pv + (size_t)t * n * Vp, row0, n_valid, Vp, nullptr, 0, scratch);
+            const uint32_t* mk = a.mask + (size_t)t * n;
+            for (int p = threadIdx.x; p < R * U; p += NT) {
+                const int r = p / U, i = p - r * U;
+                float e = -CUDART_INF_F;
+                if (r < n_valid && ((__ldg(mk + row0 + r) >> i) & 1u)) {
+                    const int src = (r / U) * U + i;
+                    float acc = 0.f;
+                    for (int kk = 0; kk < K; ++kk)
+                        acc = fmaf(sVSQ[(M + kk) * RP + src], sVSQ[(M + K + kk) * RP + r], acc);
+                    e = acc * scale;
+                }
+                sAl[i * RP + r] = e;
+            }
+            __syncthreads();
+            if (threadIdx.x < R) {
+                const int r = threadIdx.x;
+                float mx = -CUDART_INF_F;
+                for (int i = 0; i < U; ++i) mx = fmaxf(mx, sAl[i * RP + r]);
+                float den = 0.f;
+                for (int i = 0; i < U; ++i) {
+                    const float e = sAl[i * RP + r];
+                    const float p = e == -CUDART_INF_F ? 0.f : expf(e - mx);
+                    sAl[i * RP + r] = p;
+                    den += p;
+                }
+                const float inv = den > 0.f ? 1.0f / den : 0.f;
+                for (int i = 0; i < U; ++i) sAl[i * RP + r] *= inv;
+            }
+            __syncthreads();
+            for (int p = threadIdx.x; p < M * R; p += NT) {
+                const int m = p / R, r = p - m * R;
+                const int b0 = (r / U) * U;
+                float acc = 0.f;
+                if (r < n_valid)
+                    for (int i = 0; i < U; ++i) acc = fmaf(sAl[i * RP + r], sVSQ[m * RP + b0 + i], acc);
+                sC[m * RP + r] = acc;
+            }
+            __syncthreads();
+            gemm_s(wIC, H3, sC, M, sGI, H3, pg, row0, n_valid, H3, nullptr, 0, scratch);
+        } else {
+            load_tile(pg, row0, n_valid, H3, H3, sGI);
+        }
+        gemm_s(wHH, H3, sH, H, sGH, H3, nullptr, 0, 0, 0, bHH, 0, scratch);
+        if (training) {
+            if (tm) {
+                store_tile(a.sv_vsq + (size_t)t * n * Vp, row0, n_valid, Vp, Vp, sVSQ);
+                store_tile(a.sv_alpha + (size_t)t * n * U, row0, n_valid, U, U, sAl);
+                store_tile(a.sv_c + (size_t)t * n * M, row0, n_valid, M, M, sC);
+            }
+        }
+        // gates, row-major thread mapping so that the global stores are coalesced
+        float* hout = a.h_out + (size_t)t * n * H;
+        float* gt = training ? a.sv_gate + (size_t)t * n * 4 * H : nullptr;
+        for (int i = threadIdx.x; i < R * H; i += NT) {
+            const int r = i / H, ch = i - r * H;
+            const float rr = sigmoidf_(sGI[ch * RP + r] + sGH[ch * RP + r]);
+            const float zz = sigmoidf_(sGI[(H + ch) * RP + r] + sGH[(H + ch) * RP + r]);
+            const float ghn = sGH[(2 * H + ch) * RP + r];
+            const float nn = tanhf(fmaf(rr, ghn, sGI[(2 * H + ch) * RP + r]));
+            const float hp = sH[ch * RP + r];
+            const float hn = fmaf(zz, hp - nn, nn);
+            if (r < n_valid) {
+                hout[(row0 + r) * H + ch] = hn;
+                if (training) {
+                    float* g = gt + (row0 + r) * 4 * H;
+                    g[ch] = rr; g[H + ch] = zz; g[2 * H + ch] = nn; g[3 * H + ch] = ghn;
+                }
+            }
+            sGI[ch * RP + r] = hn;                 // stage h' (sH is still being read by other threads)
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < H * RP; p += NT) sH[p] = sGI[p];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Per step t (T-1 .. 0): dh = carry + dhq_t ; gates' -> dgi, dgh ; carry = dh*z + dgh W_hh ; dc = dgi W_ih[:, H:] ;
+// attention' (dc, alpha, vsq) -> dvsq.  dgi / dgh / dvsq are stashed for the batched GEMMs that follow the kernel.
+__global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
+    extern __shared__ __align__(16) float sm[];
+    const Dims d = a.d;
+    const int H = d.H, H3 = 3 * H, M = d.M, K = d.K, U = d.U, Vp = d.Vp();
+    const bool tm = d.tarmac();
+    int o = 0;
+    auto take = [&](int n) { float* p = sm + o; o += (n + 3) & ~3; return p; };
+    float* wHH = take(H3 * H);                 // [3H][H]  K-major for dgh W_hh
+    float* wIC = take(tm ? H3 * M : 0);        // [3H][M]  K-major for dgi W_ih[:, H:]
+    float* sDH = take(H * RP);
+    float* sDGI = take(H3 * RP);
+    float* sDGH = take(H3 * RP);
+    float* sDC = take(tm ? M * RP : 0);
+    float* sVSQ = take(tm ? Vp * RP : 0);
+    float* sDVSQ = take(tm ? Vp * RP : 0);
+    float* sAl = take(tm ? U * RP : 0);
+    float* sDS = take(tm ? U * RP : 0);
+    float* scratch = take(NT * 16);
+    copy_to_smem(wHH, a.w0, H3 * H);
+    if (tm) copy_to_smem(wIC, a.w1, H3 * M);
+
+    const int rpt = d.rows_per_tile();
+    const int64_t row0 = (int64_t)blockIdx.x * rpt;
+    const int n_valid = (int)min((int64_t)rpt, a.N - row0);
+    const int64_t n = a.N;
+    const float scale = tm ? 1.0f / (float)K : 0.f;
+    for (int p = threadIdx.x; p < H * RP; p += NT) sDH[p] = 0.f;
+    __syncthreads();
+
+    for (int t = a.T - 1; t >= 0; --t) {
+        const float* gt = a.sv_gate + (size_t)t * n * 4 * H;
+        const float* hprev = t > 0 ? a.h_out + (size_t)(t - 1) * n * H : a.h0;
+        const float* dhq = a.dhq + (size_t)t * n * H;
+        float* gdgi = a.st_dgi + (size_t)t * n * H3;
+        float* gdgh = a.st_dgh + (size_t)t * n * H3;
+        for (int i = threadIdx.x; i < R * H; i += NT) {
+            const int r = i / H, ch = i - r * H;
+            float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f, dir = 0.f;
+            if (r < n_valid) {
+                const float* g = gt + (row0 + r) * 4 * H;
+                const float rr = __ldg(g + ch), zz = __ldg(g + H + ch), nn = __ldg(g + 2 * H + ch), ghn = __ldg(g + H3 + ch);
+                const float gv = sDH[ch * RP + r] + __ldg(dhq + (row0 + r) * H + ch);
+                dn = gv * (1.0f - zz) * (1.0f - nn * nn);
+                dz = gv * (__ldg(hprev + (row0 + r) * H + ch) - nn) * zz * (1.0f - zz);
+                dr = dn * ghn * rr * (1.0f - rr);
+                dnr = dn * rr;
+                dir = gv * zz;
+                float* o1 = gdgi + (row0 + r) * H3;
+                float* o2 = gdgh + (row0 + r) * H3;
+                o1[ch] = dr; o1[H + ch] = dz; o1[2 * H + ch] = dn;
+                o2[ch] = dr; o2[H + ch] = dz; o2[2 * H + ch] = dnr;
+            }
+            sDGI[ch * RP + r] = dr; sDGI[(H + ch) * RP + r] = dz; sDGI[(2 * H + ch) * RP + r] = dn;
+            sDGH[ch * RP + r] = dr; sDGH[(H + ch) * RP + r] = dz; sDGH[(2 * H + ch) * RP + r] = dnr;
+            sDH[ch * RP + r] = dir;
+        }
+        __syncthreads();
+        gemm_s(wHH, H, sDGH, H3, sDH, H, nullptr, 0, 0, 0, nullptr, 2, scratch);          // carry = dh*z + dgh W_hh
+        if (tm) {
+            gemm_s(wIC, M, sDGI, H3, sDC, M, nullptr, 0, 0, 0, nullptr, 0, scratch);      // dc = dgi W_ih[:, H:]
+            load_tile(a.sv_vsq + (size_t)t * n * Vp, row0, n_valid, Vp, Vp, sVSQ);
+            load_tile(a.sv_alpha + (size_t)t * n * U, row0, n_valid, U, U, sAl);
+            __syncthreads();
+            for (int p = threadIdx.x; p < R * U; p += NT) {
+                const int r = p / U, i = p - r * U;
+                const int src = (r / U) * U + i;
+                float acc = 0.f;
+                if (r < n_valid)
+                    for (int m = 0; m < M; ++m) acc = fmaf(sDC[m * RP + r], sVSQ[m * RP + src], acc);
+                sDS[i * RP + r] = acc;
+            }
+            __syncthreads();
+            if (threadIdx.x < R) {
+                const int r = threadIdx.x;
+                float tot = 0.f;
+                for (int i = 0; i < U; ++i) tot = fmaf(sAl[i * RP + r], sDS[i * RP + r], tot);
+                for (int i = 0; i < U; ++i) sDS[i * RP + r] = sAl[i * RP + r] * (sDS[i * RP + r] - tot);
+            }
+            __syncthreads();
+            for (int p = threadIdx.x; p < Vp * R; p += NT) {
+                const int f = p / R, r = p - f * R;
+                const int b0 = (r / U) * U, li = r - b0;
+                float acc = 0.f;
+                if (r >= n_valid) {
+                } else if (f < M) {
+                    for (int j = 0; j < U; ++j) acc = fmaf(sAl[li * RP + b0 + j], sDC[f * RP + b0 + j], acc);
+                } else if (f < M + K) {
+                    for (int j = 0; j < U; ++j) acc = fmaf(sDS[li * RP + b0 + j], sVSQ[(f + K) * RP + b0 + j], acc);
+                    acc *= scale;
+                } else if (f < M + 2 * K) {
+                    for (int i = 0; i < U; ++i) acc = fmaf(sDS[i * RP + r], sVSQ[(f - K) * RP + b0 + i], acc);
+                    acc *= scale;
+                }
+                sDVSQ[f * RP + r] = acc;
+            }
+            __syncthreads();
+            store_tile(a.st_dvsq + (size_t)t * n * Vp, row0, n_valid, Vp, Vp, sDVSQ);
+        }
+        __syncthreads();
+    }
+    if (a.d_h0 != nullptr) store_tile(a.d_h0, row0, n_valid, H, H, sDH);
+}
+
+static size_t fwd_smem(const Dims& d) {
+    const int H = d.H, H3 = 3 * H, Vp = d.Vp();
+    size_t f = (size_t)H * H3 + H3 + (size_t)(H + 2 * H3) * RP + NT * 16;
+    if (d.tarmac()) f += (size_t)H * Vp + (size_t)d.M * H3 + (size_t)(Vp + d.M + d.U) * RP + 16;
+    return f * sizeof(float);
+}
+static size_t bwd_smem(const Dims& d) {
+    const int H = d.H, H3 = 3 * H, Vp = d.Vp();
+    size_t f = (size_t)H3 * H + (size_t)(H + 2 * H3) * RP + NT * 16;
+    if (d.tarmac()) f += (size_t)H3 * d.M + (size_t)(d.M + 2 * Vp + 2 * d.U) * RP + 16;
+    return f * sizeof(float);
+}
+static int check(const char* fn, const Dims& d) {
+    if (d.H < 16 || d.H % 4 || d.H > 256) { set_error("%s: hidden size %d unsupported", fn, d.H); return 2; }
+    if (d.tarmac() && (d.U < 1 || d.U > R || d.M % 4 || d.M < 4 || d.K < 1)) { set_error("%s: TarMAC shape unsupported", fn); return 2; }
+    return 0;
+}
+
+}  // namespace seq2
+}  // namespace ubs
+
+extern "C" UBS_API int64_t ubs_agent_seq2_smem_bytes(int H, int M, int K, int U, int flags, int backward) {
+    ubs::seq2::Dims d{H, (flags & UBS_STEP_TARMAC) ? M : 0, (flags & UBS_STEP_TARMAC) ? K : 0,
+                      (flags & UBS_STEP_TARMAC) ? U : 1, flags};
+    return (int64_t)(backward ? ubs::seq2::bwd_smem(d) : ubs::seq2::fwd_smem(d));
+}
+
+extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags, const float* wt_vsq_h,
+                                          const float* wt_ih_c, const float* wt_hh, const float* b_hh, const float* pv,
+                                          const float* pg, const float* h0, const uint32_t* mask, float* h_out,
+                                          float* sv_vsq, float* sv_alpha, float* sv_c, float* sv_gate, int64_t n_rows,
+                                          int n_steps, void* stream) {
+    using namespace ubs::seq2;
+    Args a{};
+    a.d = Dims{H, (flags & UBS_STEP_TARMAC) ? M : 0, (flags & UBS_STEP_TARMAC) ? K : 0, (flags & UBS_STEP_TARMAC) ? U : 1, flags};
+    if (int rc = check("ubs_agent_seq2_fwd", a.d)) return rc;
+    UBS_REQUIRE(wt_hh && b_hh && pg && h0 && h_out, "ubs_agent_seq2_fwd: NULL argument");
+    UBS_REQUIRE(!a.d.tarmac() || (wt_vsq_h && wt_ih_c && pv && mask), "ubs_agent_seq2_fwd: TarMAC arguments missing");
+    UBS_REQUIRE(!a.d.tarmac() || n_rows % a.d.U == 0, "ubs_agent_seq2_fwd: n_rows must be a multiple of agents per env");
+    UBS_REQUIRE(sv_gate == nullptr || !a.d.tarmac() || (sv_vsq && sv_alpha && sv_c), "ubs_agent_seq2_fwd: incomplete save buffers");
+    if (n_rows == 0 || n_steps == 0) return 0;
+    const size_t smem = fwd_smem(a.d);
+    if (smem > 227 * 1024) { ubs::set_error("ubs_agent_seq2_fwd: weights do not fit shared memory (%zu B)", smem); return 3; }
+    a.w0 = wt_vsq_h; a.w1 = wt_ih_c; a.w2 = wt_hh; a.b_hh = b_hh; a.pv = pv; a.pg = pg; a.h0 = h0; a.mask = mask;
+    a.h_out = h_out; a.sv_vsq = sv_vsq; a.sv_alpha = sv_alpha; a.sv_c = sv_c; a.sv_gate = sv_gate;
+    a.N = n_rows; a.T = n_steps;
+    const int rpt = a.d.rows_per_tile();
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    seq2_fwd_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), NT, smem, (cudaStream_t)stream>>>(a);
+    return ubs::check_launch("ubs_agent_seq2_fwd");
+}
+
+extern "C" UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags, const float* w_hh, const float* w_ih_c,
+                                          const float* h0, const float* h_out, const float* sv_vsq,
+                                          const float* sv_alpha, const float* sv_gate, const float* dhq, float* st_dgi,
+                                          float* st_dgh, float* st_dvsq, float* d_h0, int64_t n_rows, int n_steps,
+                                          void* stream) {
+    using namespace ubs::seq2;
+    Args a{};
+    a.d = Dims{H, (flags & UBS_STEP_TARMAC) ? M : 0, (flags & UBS_STEP_TARMAC) ? K : 0, (flags & UBS_STEP_TARMAC) ? U : 1, flags};
+    if (int rc = check("ubs_agent_seq2_bwd", a.d)) return rc;
+    UBS_REQUIRE(w_hh && h0 && h_out && sv_gate && dhq && st_dgi && st_dgh, "ubs_agent_seq2_bwd: NULL argument");
+    UBS_REQUIRE(!a.d.tarmac() || (w_ih_c && sv_vsq && sv_alpha && st_dvsq), "ubs_agent_seq2_bwd: TarMAC arguments missing");
+    if (n_rows == 0 || n_steps == 0) return 0;
+    const size_t smem = bwd_smem(a.d);
+    if (smem > 227 * 1024) { ubs::set_error("ubs_agent_seq2_bwd: weights do not fit shared memory (%zu B)", smem); return 3; }
+    a.w0 = w_hh; a.w1 = w_ih_c; a.h0 = h0; a.h_out = const_cast<float*>(h_out);
+    a.sv_vsq = const_cast<float*>(sv_vsq); a.sv_alpha = const_cast<float*>(sv_alpha); a.sv_gate = const_cast<float*>(sv_gate);
+    a.dhq = dhq; a.st_dgi = st_dgi; a.st_dgh = st_dgh; a.st_dvsq = st_dvsq; a.d_h0 = d_h0; a.N = n_rows; a.T = n_steps;
+    const int rpt = a.d.rows_per_tile();
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(seq2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    seq2_bwd_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), NT, smem, (cudaStream_t)stream>>>(a);
+    return ubs::check_launch("ubs_agent_seq2_bwd");
+}

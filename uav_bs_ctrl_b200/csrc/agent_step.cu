@@ -149,11 +149,14 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ W, int ldw, 
                     const int k = kb + KB + i;
                     wn[i] = (k < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw)) : zero4;
                 }
+                float4 xa[KB];                                  // all shared loads of the block first (~30-cycle latency)
+#pragma unroll
+                for (int i = 0; i < KB; ++i)
+                    xa[i] = *reinterpret_cast<const float4*>(ap + min(kb + i, k1 - 1) * RP);   // rows past k1: zero weights
 #pragma unroll
                 for (int i = 0; i < KB; ++i) {
-                    const int k = min(kb + i, k1 - 1);          // rows past k1 carry zero weights
                     const float4 w = wc[i];
-                    const float4 x = *reinterpret_cast<const float4*>(ap + k * RP);
+                    const float4 x = xa[i];
                     acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
                     acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
                     acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);

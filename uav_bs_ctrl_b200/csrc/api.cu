@@ -19,3 +19,4 @@ extern "C" UBS_API int ubs_version(void) { return UBS_GNN_VERSION; }
 extern "C" UBS_API const char* ubs_last_error(void) { return ubs::g_err; }
 extern "C" UBS_API int64_t ubs_launch_count(void) { return (int64_t)ubs::g_launches.load(); }
 extern "C" UBS_API void ubs_reset_launch_count(void) { ubs::g_launches.store(0); }
+extern "C" UBS_API void ubs_add_launch_count(int64_t n) { ubs::g_launches.fetch_add((long long)n); }

@@ -23,7 +23,7 @@ import torch as th
 import torch.nn as nn
 from torch.optim import AdamW
 
-from . import dist
+from . import dist, _lib
 from .agents import REGISTRY as agent_REGISTRY, DRQN_REGISTRY
 from .graph import HeteroGraph, batch as graph_batch
 
@@ -281,10 +281,13 @@ class MultiAgentQLearner:
                 self._act_arena_eager(arena, t)          # warm-up outside capture
             th.cuda.current_stream().wait_stream(side)
             g = th.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with th.cuda.graph(g):
                 self._act_arena_eager(arena, t)
+            g = (g, _lib.launch_count() - n0)             # library kernels inside the graph (for the launch counter)
             self._act_graphs[key] = g
-        g.replay()
+        g[0].replay()
+        _lib.add_launches(g[1])
         return arena.acts[t]
 
     def update_arena(self, arena, sync=True):

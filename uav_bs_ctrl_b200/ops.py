@@ -431,3 +431,130 @@ class SegmentEncode(th.autograd.Function):
                 grads.append(gparams[o:o + n].view(shapes[k]) if has[k] else None)
                 o += n
         return (None,) * 11 + tuple(grads)
+
+
+# ====================================================================================================================
+# Sequence path v2: batched GEMMs for everything that depends on the observation only + a persistent kernel whose
+# recurrent weights stay in shared memory (ubs_agent_seq2_fwd / ubs_agent_seq2_bwd).
+def seq2_supported(dims: AgentDims) -> bool:
+    lib = _lib.load()
+    if not dims.supported():
+        return False
+    return max(int(lib.ubs_agent_seq2_smem_bytes(dims.H, dims.M, dims.K, dims.U, dims.flags, b)) for b in (0, 1)) <= 227 * 1024
+
+
+def _vsq_weights(params, dims):
+    """Concatenated ``[W_val; W_sign; W_que]`` (Vp, 2H) and bias (Vp), zero padded to a multiple of 4 rows."""
+    w = th.cat((params["W_val"], params["W_sign"], params["W_que"]), 0)
+    b = th.cat((params["b_val"], params["b_sign"], params["b_que"]), 0)
+    if dims.Vp != dims.V:
+        w = th.cat((w, w.new_zeros(dims.Vp - dims.V, w.shape[1])), 0)
+        b = th.cat((b, b.new_zeros(dims.Vp - dims.V)), 0)
+    return w, b
+
+
+def _seq2_forward(dims, params, xg, h0, mask, training):
+    lib = _lib.load()
+    T, N = xg.shape[0], xg.shape[1]
+    TN, H, M, K, U, Vp = T * N, dims.H, dims.M, dims.K, dims.U, dims.Vp
+    f32 = dict(dtype=th.float32, device=xg.device)
+    xg2 = xg.reshape(TN, dims.Fin)
+    x = th.relu_(th.addmm(params["b_aggr"], xg2, params["W_aggr"].t())) if dims.aggr else xg2
+    W_ih, W_hh = params["W_ih"], params["W_hh"]
+    pg = th.addmm(params["b_ih"], x, W_ih[:, :H].t())
+    wt_hh = W_hh.t().contiguous()
+    Wv = pv = wt_vsq_h = wt_ih_c = None
+    if dims.tarmac:
+        Wv, bv = _vsq_weights(params, dims)
+        pv = th.addmm(bv, x, Wv[:, :H].t())
+        wt_vsq_h = Wv[:, H:].t().contiguous()
+        wt_ih_c = W_ih[:, H:].t().contiguous()
+    h_out = th.empty(T, N, H, **f32)
+    sv_gate = th.empty(T, N, 4 * H, **f32) if training else None
+    sv_vsq = th.empty(T, N, Vp, **f32) if training and dims.tarmac else None
+    sv_alpha = th.empty(T, N, U, **f32) if training and dims.tarmac else None
+    sv_c = th.empty(T, N, M, **f32) if training and dims.tarmac else None
+    P = _lib.ptr
+    with _timed("agent_seq2_fwd", (T, N, dims.ints(), training)):
+        _lib.check(lib.ubs_agent_seq2_fwd(H, M, K, U, dims.flags, P(wt_vsq_h), P(wt_ih_c), P(wt_hh), P(params["b_hh"]),
+                                          P(pv), P(pg), P(h0), P(mask), P(h_out), P(sv_vsq), P(sv_alpha), P(sv_c),
+                                          P(sv_gate), N, T, _lib.stream()), "ubs_agent_seq2_fwd")
+    q = th.addmm(params["b_out"], h_out.view(TN, H), params["W_out"].t()).view(T, N, dims.A)
+    return q, h_out, (x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate)
+
+
+def agent_seq2_infer(dims: AgentDims, params: dict, xg, h0, mask):
+    """Inference through the resident-weight sequence kernel: returns ``q (T,N,A)``, ``h_out (T,N,H)``."""
+    _lib.require_cuda(xg, h0)
+    p = {k: (None if v is None else v.detach()) for k, v in params.items()}
+    q, h_out, _ = _seq2_forward(dims, p, _f32c(xg), _f32c(h0), mask, False)
+    return q, h_out
+
+
+class AgentSequence2(th.autograd.Function):
+    """Same contract as :class:`AgentSequence` (``forward(xg, h0, mask, dims, *params[PARAM_ORDER])`` ->
+    ``(q, h_last, h_all)``) on the resident-weight kernels."""
+
+    @staticmethod
+    def forward(ctx, xg, h0, mask, dims, *params):
+        _lib.require_cuda(xg, h0)
+        xg, h0 = _f32c(xg), _f32c(h0)
+        p = {k: (None if v is None else _f32c(v.detach())) for k, v in zip(PARAM_ORDER, params)}
+        q, h_out, (x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate) = _seq2_forward(dims, p, xg, h0, mask, True)
+        ctx.dims = dims
+        ctx.has = [v is not None for v in params]
+        ctx.save_for_backward(xg, h0, h_out, x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate, *[v for v in p.values() if v is not None])
+        ctx.mark_non_differentiable(h_out)
+        return q, h_out[-1].clone(), h_out
+
+    @staticmethod
+    def backward(ctx, dq, dh_last, _dh_all):
+        xg, h0, h_out, x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate, *plist = ctx.saved_tensors
+        dims = ctx.dims
+        it = iter(plist)
+        p = {k: (next(it) if has else None) for k, has in zip(PARAM_ORDER, ctx.has)}
+        lib = _lib.load()
+        T, N = xg.shape[0], xg.shape[1]
+        TN, H, M, K, U, A, V, Vp = T * N, dims.H, dims.M, dims.K, dims.U, dims.A, dims.V, dims.Vp
+        f32 = dict(dtype=th.float32, device=xg.device)
+        dq2 = (_f32c(dq) if dq is not None else th.zeros(T, N, A, **f32)).view(TN, A)
+        dhq = (dq2 @ p["W_out"]).view(T, N, H)
+        if dh_last is not None:
+            dhq[T - 1] += dh_last
+        W_ih, W_hh = p["W_ih"], p["W_hh"]
+        w_ih_c = W_ih[:, H:].contiguous() if dims.tarmac else None
+        st_dgi, st_dgh = th.empty(T, N, 3 * H, **f32), th.empty(T, N, 3 * H, **f32)
+        st_dvsq = th.empty(T, N, Vp, **f32) if dims.tarmac else None
+        d_h0 = th.empty_like(h0) if ctx.needs_input_grad[1] else None
+        P = _lib.ptr
+        with _timed("agent_seq2_bwd", (T, N, dims.ints(), True)):
+            _lib.check(lib.ubs_agent_seq2_bwd(H, M, K, U, dims.flags, P(W_hh), P(w_ih_c), P(h0), P(h_out), P(sv_vsq),
+                                              P(sv_alpha), P(sv_gate), P(dhq), P(st_dgi), P(st_dgh), P(st_dvsq),
+                                              P(d_h0), N, T, _lib.stream()), "ubs_agent_seq2_bwd")
+        dgi, dgh = st_dgi.view(TN, 3 * H), st_dgh.view(TN, 3 * H)
+        hprev = th.cat((h0.unsqueeze(0), h_out[:-1]), 0).view(TN, H)
+        g = {}
+        g["W_out"], g["b_out"] = dq2.t() @ h_out.view(TN, H), dq2.sum(0)
+        g["W_hh"], g["b_hh"] = dgh.t() @ hprev, dgh.sum(0)
+        g["b_ih"] = dgi.sum(0)
+        dx = dgi @ W_ih[:, :H]
+        if dims.tarmac:
+            dv = st_dvsq.view(TN, Vp)
+            g["W_ih"] = th.cat((dgi.t() @ x, dgi.t() @ sv_c.view(TN, M)), 1)
+            gw = th.cat((dv.t() @ x, dv.t() @ hprev), 1)
+            gb = dv.sum(0)
+            g["W_val"], g["b_val"] = gw[:M], gb[:M]
+            g["W_sign"], g["b_sign"] = gw[M:M + K], gb[M:M + K]
+            g["W_que"], g["b_que"] = gw[M + K:V], gb[M + K:V]
+            dx.addmm_(dv, Wv[:, :H])
+        else:
+            g["W_ih"] = dgi.t() @ x
+        if dims.aggr:
+            dpre = dx.mul_(x > 0)
+            xg2 = xg.view(TN, dims.Fin)
+            g["W_aggr"], g["b_aggr"] = dpre.t() @ xg2, dpre.sum(0)
+            d_xg = (dpre @ p["W_aggr"]).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
+        else:
+            d_xg = dx.view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
+        grads = tuple(g.get(k) if has else None for k, has in zip(PARAM_ORDER, ctx.has))
+        return (d_xg, d_h0, None, None) + grads

@@ -98,6 +98,23 @@ UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst, const int3
                       int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout,
                       int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
 
+/* ---- GATv2 attention + aggregation on pre-projected features, general CSR (wide inputs / synthetic sweep) ---------
+ * After the library GEMMs el = fc_src(h_src) (n_src,H), er = fc_dst(h_dst) (n_dst,H), res = res_fc(h_dst) (nullable):
+ *   out[v] = act( sum_e softmax_e( <attn_k, leaky_relu(el[u_e] + er[v])_k> ) * el[u_e] + res[v] ),  H = heads*D in
+ * {32,64,128,256}.  One gather pass over the edges (coalesced full-row loads, online softmax); nothing of size E x H
+ * is materialised.  Backward: grad_el (n_src,H; the caller zero-fills it when src_idx != NULL — vector atomics),
+ * grad_er (n_dst,H), grad_res (n_dst,H, nullable) = grad_out * 1[out > 0], grad_attn (H) via a fixed-order two-stage
+ * reduction (workspace: ubs_gat_aggr_bwd_workspace floats).                                                      */
+UBS_API int ubs_gat_aggr_fwd(const float* el, const float* er, const float* res, const int32_t* indptr,
+                     const int32_t* src_idx, const float* attn, float* out, float* smax, float* ssum,
+                     int64_t n_dst, int64_t n_edges, int heads, int D, float negative_slope, int flags, void* stream);
+UBS_API int64_t ubs_gat_aggr_bwd_workspace(int64_t n_dst, int heads, int D);
+UBS_API int ubs_gat_aggr_bwd(const float* el, const float* er, const float* res, const int32_t* indptr,
+                     const int32_t* src_idx, const float* attn, const float* out, const float* grad_out,
+                     const float* smax, const float* ssum, float* grad_el, float* grad_er, float* grad_res,
+                     float* grad_attn, float* workspace, int64_t n_dst, int64_t n_edges, int heads, int D,
+                     float negative_slope, int flags, void* stream);
+
 /* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
  * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
  * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.
@@ -148,6 +165,15 @@ UBS_API int ubs_agent_seq_fwd(int H, int M, int K, int A, int U, int Fin, int fl
                       float* h_out, float* q, int64_t* actions,
                       float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
                       int64_t n_rows, int n_steps, void* stream);
+/* Same kernel with epsilon-greedy action selection fused in (reference learner.act, algos/madrqn/learner.py:75-78):
+ * actions[t,r] = eg_u[t,r] <= *eg_eps ? eg_a[t,r] : argmax_a q[t,r,a].  eg_u (n_steps,n_rows) uniforms (one draw per
+ * env, repeated for its agents), eg_a (n_steps,n_rows) int64 random actions, eg_eps device scalar; all NULL = greedy. */
+UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int Fin, int flags, const float* packed,
+                      const float* xin, const float* h0, const uint32_t* mask,
+                      float* h_out, float* q, int64_t* actions,
+                      const float* eg_u, const int64_t* eg_a, const float* eg_eps,
+                      float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
+                      int64_t n_rows, int n_steps, void* stream);
 /* Reverse-time walk.  dq (n_steps,n_rows,A) and dh_last (n_rows,H, nullable) come from the loss; outputs:
  * d_xin (n_steps,n_rows,Fin), d_h0 (nullable) and the stashes st_dgi/st_dgh (.., 3H), st_dvsq (.., round4(M+2K)),
  * st_dpre (.., H) from which the caller forms the parameter gradients with batched GEMMs over the whole sequence. */
@@ -161,7 +187,7 @@ UBS_API int ubs_agent_seq_bwd(int H, int M, int K, int A, int U, int Fin, int fl
  * Same math as ubs_agent_seq_*, split along the one true dependency of a BPTT window.  The caller computes, for all
  * n_steps*n_rows rows at once (batched GEMMs; the encoder does not depend on h, gnn_agents.py:53):
  *     x = relu(W_aggr xin + b_aggr),  pv = W_vsq[:, :H] x + b_vsq  (n_steps,n_rows,round4(M+2K)),
- *     pg = W_ih[:, :H] x + b_ih  (n_steps,n_rows,3H)
+ *     pg = W_ih[:, :H] x + b_ih  (n_steps,n_rows,3H)         [row strides ld_pv / ld_pg: one fused GEMM output]
  * and afterwards the Q head, the x-path gradients and every parameter gradient.  The kernel keeps
  *     wt_vsq_h = W_vsq[:, H:]^T (H, round4(M+2K)), wt_ih_c = W_ih[:, H:]^T (M, 3H), wt_hh = W_hh^T (H, 3H), b_hh
  * in shared memory for the whole sequence (backward: w_hh (3H,H) and w_ih_c = W_ih[:, H:] (3H,M), original layouts).
@@ -170,13 +196,14 @@ UBS_API int64_t ubs_agent_seq2_smem_bytes(int H, int M, int K, int U, int flags,
 UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags, const float* wt_vsq_h, const float* wt_ih_c,
                        const float* wt_hh, const float* b_hh, const float* pv, const float* pg, const float* h0,
                        const uint32_t* mask, float* h_out, float* sv_vsq, float* sv_alpha, float* sv_c,
-                       float* sv_gate, int64_t n_rows, int n_steps, void* stream);
+                       float* sv_gate, int64_t ld_pv, int64_t ld_pg, int64_t n_rows, int n_steps, void* stream);
 /* dhq (n_steps,n_rows,H) = dq W_out (+ grad of the last hidden state on the last step).  Outputs the stashes
- * st_dgi / st_dgh (.., 3H), st_dvsq (.., round4(M+2K)) and d_h0 (nullable).                                      */
+ * st_dgi / st_dgh (.., 3H), st_dvsq (.., round4(M+2K)) — three column blocks of row stride ld_stash, so they can
+ * share one buffer [dgi | dvsq | dgh] that feeds the batched GEMMs without copies — and d_h0 (nullable).            */
 UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags, const float* w_hh, const float* w_ih_c,
                        const float* h0, const float* h_out, const float* sv_vsq, const float* sv_alpha,
                        const float* sv_gate, const float* dhq, float* st_dgi, float* st_dgh, float* st_dvsq,
-                       float* d_h0, int64_t n_rows, int n_steps, void* stream);
+                       float* d_h0, int64_t ld_stash, int64_t n_rows, int n_steps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ def edge_softmax(dst: th.Tensor, e: th.Tensor, n_dst: int) -> th.Tensor:
 
 
 def gatv2_conv(src, dst, n_dst, feat_src, feat_dst, fc_src_w, fc_src_b, fc_dst_w, fc_dst_b, attn,
-               res_w=None, res_b=None, negative_slope=0.2, activation=F.relu):
+               res_w=None, res_b=None, negative_slope=0.2, activation=F.relu, identity_res=False):
     """DGL 0.9.0 ``GATv2Conv.forward`` with a (src, dst) feature pair, ``feat_drop = attn_drop = 0``:
 
         el = fc_src(h_src)            er = fc_dst(h_dst)                 (views (·, heads, D))
@@ -63,6 +63,8 @@ def gatv2_conv(src, dst, n_dst, feat_src, feat_dst, fc_src_w, fc_src_b, fc_dst_w
     rst = th.zeros(n_dst, heads, D, dtype=m.dtype, device=m.device).index_add_(0, dst, m)
     if res_w is not None:
         rst = rst + F.linear(feat_dst, res_w, res_b).view(n_dst, heads, D)
+    elif identity_res:          # res_fc = Identity(): h_dst viewed (N, -1, out_feats) = (N, 1, D), broadcast over heads
+        rst = rst + feat_dst.view(n_dst, -1, D)
     if activation is not None:
         rst = activation(rst)
     return rst
@@ -144,13 +146,11 @@ class GATv2Conv(nn.Module):
             raise RuntimeError("There are 0-in-degree nodes in the graph")
         if isinstance(self.res_fc, nn.Linear):
             rw, rb = self.res_fc.weight, self.res_fc.bias
-        elif isinstance(self.res_fc, nn.Identity):
-            rw = th.eye(self._num_heads * self._out_feats, h_dst.shape[1], dtype=h_dst.dtype, device=h_dst.device)
-            rb = None
         else:
             rw = rb = None
         return gatv2_conv(src, dst, n_dst, h_src, h_dst, self.fc_src.weight, self.fc_src.bias,
-                          self.fc_dst.weight, self.fc_dst.bias, self.attn, rw, rb, self._slope, self.activation)
+                          self.fc_dst.weight, self.fc_dst.bias, self.attn, rw, rb, self._slope, self.activation,
+                          identity_res=isinstance(self.res_fc, nn.Identity))
 
 
 class DuelingLayer(nn.Module):

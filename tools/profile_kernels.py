@@ -127,6 +127,20 @@ def main():
     timeit(f"agent sequence backward incl. weight-grad GEMMs[{T} steps]",
            lambda: th.autograd.grad(q, [xinT] + [p for p in plist if p is not None], gq, retain_graph=True))
     timeit("agent_pack", lambda: ops.agent_pack(dims, params))
+    # resident-weight sequence kernels (+ their batched GEMMs)
+    if ops.seq2_supported(dims):
+        ops.TIMER = ops.KernelTimer()
+        timeit(f"seq2 forward incl. batched GEMMs[{T} steps,train]", lambda: ops.AgentSequence2.apply(xinT, h0, maskT, dims, *plist))
+        q2, _, _ = ops.AgentSequence2.apply(xinT, h0, maskT, dims, *plist)
+        gq2 = th.randn_like(q2)
+        timeit(f"seq2 backward incl. batched GEMMs[{T} steps]",
+               lambda: th.autograd.grad(q2, [xinT] + [p for p in plist if p is not None], gq2, retain_graph=True))
+        summ = ops.TIMER.summary()
+        ops.TIMER = None
+        for k in ("agent_seq2_fwd", "agent_seq2_bwd"):
+            if k in summ:
+                results[f"{k}[{T} steps] (kernel only, L2 flushed before the enclosing op)"] = {
+                    "avg_us": 1e3 * summ[k]["ms"] / summ[k]["count"]}
     if not a.ncu:
         print(json.dumps({"shape": {"B": B, "U": U, "G": G, "H": H, "T": T}, "kernels": results}, indent=1))
 

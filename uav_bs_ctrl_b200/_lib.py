@@ -36,12 +36,16 @@ _PROTOS = {
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),
     "ubs_gatv2_seg_bwd": (C.c_int, [_F] * 19 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
+    "ubs_gat_aggr_fwd": (C.c_int, [_F] * 9 + [_i64, _i64, _int, _int, _flt, _int, _ptr]),
+    "ubs_gat_aggr_bwd_workspace": (_i64, [_i64, _int, _int]),
+    "ubs_gat_aggr_bwd": (C.c_int, [_F] * 15 + [_i64, _i64, _int, _int, _flt, _int, _ptr]),
     "ubs_agent_seq2_smem_bytes": (_i64, [_int] * 6),
-    "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _int, _ptr]),
-    "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _int, _ptr]),
+    "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _i64, _i64, _int, _ptr]),
+    "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _i64, _int, _ptr]),
     "ubs_agent_pack_size": (_i64, [_int] * 7),
     "ubs_agent_pack": (C.c_int, [_int] * 7 + [_F] * 15 + [_ptr]),
     "ubs_agent_seq_fwd": (C.c_int, [_int] * 7 + [_F] * 11 + [_i64, _int, _ptr]),
+    "ubs_agent_act_fwd": (C.c_int, [_int] * 7 + [_F] * 14 + [_i64, _int, _ptr]),
     "ubs_agent_seq_bwd": (C.c_int, [_int] * 7 + [_F] * 15 + [_i64, _int, _ptr]),
 }
 

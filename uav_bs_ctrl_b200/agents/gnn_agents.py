@@ -51,7 +51,7 @@ class GATv2Conv(nn.Module):
             if self._in_dst_feats != out_feats:
                 self.res_fc = nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=bias)
             else:
-                raise NotImplementedError("identity residual (in_dst_feats == out_feats) never occurs on this path")
+                self.res_fc = nn.Identity()          # DGL: h_dst viewed (N, 1, out_feats), broadcast over the heads
         else:
             self.register_buffer("res_fc", None)
         self.activation = activation
@@ -89,9 +89,23 @@ class GATv2Conv(nn.Module):
         flags |= ops.GAT_RESIDUAL if has_res else 0
         if not ops.gatv2_fused_supported(self._in_src_feats, self._in_dst_feats, self._num_heads, self._out_feats,
                                          self._negative_slope):
-            raise NotImplementedError(
-                f"GATv2Conv shape (F_src={self._in_src_feats}, F_dst={self._in_dst_feats}, heads={self._num_heads}, "
-                f"D={self._out_feats}) is outside the fused kernel's range")
+            # wide inputs (synthetic sweep): dense projections by library GEMMs, then ONE gather/softmax/aggregate pass
+            if not ops.gat_aggregate_supported(self._num_heads, self._out_feats, self._negative_slope):
+                raise NotImplementedError(
+                    f"GATv2Conv shape (F_src={self._in_src_feats}, F_dst={self._in_dst_feats}, "
+                    f"heads={self._num_heads}, D={self._out_feats}) is outside the kernels' range")
+            el = F.linear(h_src, self.fc_src.weight, self.fc_src.bias)
+            er = F.linear(h_dst, self.fc_dst.weight, self.fc_dst.bias)
+            if has_res:
+                rs = F.linear(h_dst, self.res_fc.weight, self.res_fc.bias)
+            elif isinstance(self.res_fc, nn.Identity):
+                rs = h_dst.repeat(1, self._num_heads)
+            else:
+                rs = None
+            out = ops.GATAggregate.apply(el, er, rs, csr.indptr, csr.src_idx, self.attn, self._num_heads,
+                                         self._out_feats, self._negative_slope, flags & ops.GAT_RELU)
+            out = out.view(-1, self._num_heads, self._out_feats)
+            return post(out) if post is not None else out
         out = ops.GATv2Fused.apply(h_src, h_dst, csr.indptr, csr.src_idx, self.fc_src.weight, self.fc_src.bias,
                                    self.fc_dst.weight, self.fc_dst.bias, self.attn,
                                    self.res_fc.weight if has_res else None, self.res_fc.bias if has_res else None,
@@ -301,6 +315,7 @@ class GnnAgent(nn.Module):
         self._n_rounds = getattr(args, "n_rounds", 1)
         self._pack_cache = {}
         self.use_seq2 = True          # resident-weight sequence kernels when they fit (False: weight-streaming kernels)
+        self.use_seq2_act = False     # act step through the resident-weight kernel (T = 1) instead of the streaming one
 
     def init_hidden(self):
         return th.zeros(1, self._hidden_size)
@@ -429,16 +444,26 @@ class GnnAgent(nn.Module):
         return self._run_sequence(dims, xin, h0.contiguous(), mask)
 
     @th.no_grad()
-    def arena_step(self, arena, t, q_out=None):
+    def arena_step(self, arena, t, q_out=None, explore=None):
         """Inference on slot t: reads ``arena.h[t]``, writes ``arena.h[t+1]`` and the greedy actions ``arena.acts[t]``;
         returns the Q values.  Three launches (two relations + the fused step), no allocation-dependent host logic,
         so the call can be captured in a CUDA graph."""
         dims = self.arena_dims(arena)
-        packed = self._packed(dims, self._fused_params())
         xin = self._arena_xin(arena, t, 1)
         mask = arena.sec("mask", t) if dims.tarmac else None
+        if self.use_seq2_act and self.use_seq2 and ops.seq2_supported(dims):
+            # two small library GEMMs (aggregator; fused [pv | pg]) + the resident-weight kernel with T = 1 + Q head
+            q, h_all = ops.agent_seq2_infer(dims, self._fused_params(), xin, arena.h[t], mask)
+            arena.h[t + 1].copy_(h_all[0])
+            th.argmax(q[0], 1, out=arena.acts[t])
+            if explore is not None:
+                th.where(explore[0] <= explore[2], explore[1], arena.acts[t], out=arena.acts[t])
+            if q_out is not None:
+                q_out.copy_(q)
+            return q[0]
+        packed = self._packed(dims, self._fused_params())
         q, _, _ = ops.agent_seq_infer(dims, packed, xin, arena.h[t], mask, h_out=arena.h[t + 1].unsqueeze(0),
-                                      q=q_out, acts=arena.acts[t].unsqueeze(0))
+                                      q=q_out, acts=arena.acts[t].unsqueeze(0), explore=explore)
         return q[0]
 
     def forward(self, g, h):

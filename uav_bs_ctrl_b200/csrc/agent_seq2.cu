@@ -17,7 +17,10 @@
 namespace ubs {
 namespace seq2 {
 
-constexpr int R = 16, RP = 20, NT = 256;
+#ifndef UBS_SEQ2_NT
+#define UBS_SEQ2_NT 512
+#endif
+constexpr int R = 16, RP = 20, NT = UBS_SEQ2_NT;   // 16 warps per CTA: the only latency hiding a 1-CTA-per-SM kernel has
 
 struct Dims {
     int H, M, K, U, flags;
@@ -135,6 +138,7 @@ struct Args {
     float* h_out; float* sv_vsq; float* sv_alpha; float* sv_c; float* sv_gate;
     // backward
     const float* dhq; float* st_dgi; float* st_dgh; float* st_dvsq; float* d_h0;
+    int64_t ld_pv, ld_pg, ld_st;       // row strides (floats) of pv / pg and of the three stash pointers
     int64_t N; int T;
 };
 
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(NT) seq2_fwd_kernel(const Args a) {
     __syncthreads();
 
     for (int t = 0; t < a.T; ++t) {
-        const float* pg = a.pg + (size_t)t * n * H3;
+        const float* pg = a.pg + (size_t)t * n * a.ld_pg;
         if (tm) {
-            gemm_s(wVH, Vp, sH, H, sVSQ, Vp, a.pv + (size_t)t * n * Vp, row0, n_valid, Vp, nullptr, 0, scratch);
+            gemm_s(wVH, Vp, sH, H, sVSQ, Vp, a.pv + (size_t)t * n * a.ld_pv, row0, n_valid, a.ld_pv, nullptr, 0, scratch);
             const uint32_t* mk = a.mask + (size_t)t * n;
             for (int p = threadIdx.x; p < R * U; p += NT) {
                 const int r = p / U, i = p - r * U;
@@ -212,9 +216,9 @@ __global__ void __launch_bounds__(NT) seq2_fwd_kernel(const Args a) {
                 sC[m * RP + r] = acc;
             }
             __syncthreads();
-            gemm_s(wIC, H3, sC, M, sGI, H3, pg, row0, n_valid, H3, nullptr, 0, scratch);
+            gemm_s(wIC, H3, sC, M, sGI, H3, pg, row0, n_valid, a.ld_pg, nullptr, 0, scratch);
         } else {
-            load_tile(pg, row0, n_valid, H3, H3, sGI);
+            load_tile(pg, row0, n_valid, H3, a.ld_pg, sGI);
         }
         gemm_s(wHH, H3, sH, H, sGH, H3, nullptr, 0, 0, 0, bHH, 0, scratch);
         if (training) {
@@ -286,8 +290,8 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
         const float* gt = a.sv_gate + (size_t)t * n * 4 * H;
         const float* hprev = t > 0 ? a.h_out + (size_t)(t - 1) * n * H : a.h0;
         const float* dhq = a.dhq + (size_t)t * n * H;
-        float* gdgi = a.st_dgi + (size_t)t * n * H3;
-        float* gdgh = a.st_dgh + (size_t)t * n * H3;
+        float* gdgi = a.st_dgi + (size_t)t * n * a.ld_st;
+        float* gdgh = a.st_dgh + (size_t)t * n * a.ld_st;
         for (int i = threadIdx.x; i < R * H; i += NT) {
             const int r = i / H, ch = i - r * H;
             float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f, dir = 0.f;
@@ -300,8 +304,8 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
                 dr = dn * ghn * rr * (1.0f - rr);
                 dnr = dn * rr;
                 dir = gv * zz;
-                float* o1 = gdgi + (row0 + r) * H3;
-                float* o2 = gdgh + (row0 + r) * H3;
+                float* o1 = gdgi + (row0 + r) * a.ld_st;
+                float* o2 = gdgh + (row0 + r) * a.ld_st;
                 o1[ch] = dr; o1[H + ch] = dz; o1[2 * H + ch] = dn;
                 o2[ch] = dr; o2[H + ch] = dz; o2[2 * H + ch] = dnr;
             }
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
                 sDVSQ[f * RP + r] = acc;
             }
             __syncthreads();
-            store_tile(a.st_dvsq + (size_t)t * n * Vp, row0, n_valid, Vp, Vp, sDVSQ);
+            store_tile(a.st_dvsq + (size_t)t * n * a.ld_st, row0, n_valid, Vp, a.ld_st, sDVSQ);
         }
         __syncthreads();
     }
@@ -386,8 +390,8 @@ extern "C" UBS_API int64_t ubs_agent_seq2_smem_bytes(int H, int M, int K, int U,
 extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags, const float* wt_vsq_h,
                                           const float* wt_ih_c, const float* wt_hh, const float* b_hh, const float* pv,
                                           const float* pg, const float* h0, const uint32_t* mask, float* h_out,
-                                          float* sv_vsq, float* sv_alpha, float* sv_c, float* sv_gate, int64_t n_rows,
-                                          int n_steps, void* stream) {
+                                          float* sv_vsq, float* sv_alpha, float* sv_c, float* sv_gate, int64_t ld_pv,
+                                          int64_t ld_pg, int64_t n_rows, int n_steps, void* stream) {
     using namespace ubs::seq2;
     Args a{};
     a.d = Dims{H, (flags & UBS_STEP_TARMAC) ? M : 0, (flags & UBS_STEP_TARMAC) ? K : 0, (flags & UBS_STEP_TARMAC) ? U : 1, flags};
@@ -401,7 +405,9 @@ extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags,
     if (smem > 227 * 1024) { ubs::set_error("ubs_agent_seq2_fwd: weights do not fit shared memory (%zu B)", smem); return 3; }
     a.w0 = wt_vsq_h; a.w1 = wt_ih_c; a.w2 = wt_hh; a.b_hh = b_hh; a.pv = pv; a.pg = pg; a.h0 = h0; a.mask = mask;
     a.h_out = h_out; a.sv_vsq = sv_vsq; a.sv_alpha = sv_alpha; a.sv_c = sv_c; a.sv_gate = sv_gate;
-    a.N = n_rows; a.T = n_steps;
+    a.N = n_rows; a.T = n_steps; a.ld_pv = ld_pv; a.ld_pg = ld_pg;
+    UBS_REQUIRE(ld_pg >= 3 * H && ld_pg % 4 == 0 && (!a.d.tarmac() || (ld_pv >= a.d.Vp() && ld_pv % 4 == 0)), "ubs_agent_seq2_fwd: bad leading dimensions");
+    UBS_REQUIRE(((uintptr_t)pg % 16) == 0 && ((uintptr_t)pv % 16) == 0, "ubs_agent_seq2_fwd: pv / pg must be 16-byte aligned");
     const int rpt = a.d.rows_per_tile();
     static size_t configured = 0;
     if (smem > configured) {
@@ -415,8 +421,8 @@ extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags,
 extern "C" UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags, const float* w_hh, const float* w_ih_c,
                                           const float* h0, const float* h_out, const float* sv_vsq,
                                           const float* sv_alpha, const float* sv_gate, const float* dhq, float* st_dgi,
-                                          float* st_dgh, float* st_dvsq, float* d_h0, int64_t n_rows, int n_steps,
-                                          void* stream) {
+                                          float* st_dgh, float* st_dvsq, float* d_h0, int64_t ld_stash, int64_t n_rows,
+                                          int n_steps, void* stream) {
     using namespace ubs::seq2;
     Args a{};
     a.d = Dims{H, (flags & UBS_STEP_TARMAC) ? M : 0, (flags & UBS_STEP_TARMAC) ? K : 0, (flags & UBS_STEP_TARMAC) ? U : 1, flags};
@@ -429,6 +435,8 @@ extern "C" UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags,
     a.w0 = w_hh; a.w1 = w_ih_c; a.h0 = h0; a.h_out = const_cast<float*>(h_out);
     a.sv_vsq = const_cast<float*>(sv_vsq); a.sv_alpha = const_cast<float*>(sv_alpha); a.sv_gate = const_cast<float*>(sv_gate);
     a.dhq = dhq; a.st_dgi = st_dgi; a.st_dgh = st_dgh; a.st_dvsq = st_dvsq; a.d_h0 = d_h0; a.N = n_rows; a.T = n_steps;
+    a.ld_st = ld_stash;
+    UBS_REQUIRE(ld_stash >= 3 * H, "ubs_agent_seq2_bwd: bad stash leading dimension");
     const int rpt = a.d.rows_per_tile();
     static size_t configured = 0;
     if (smem > configured) {

@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(256) agent_pack_kernel(const PackArgs a) {
 // out[j*RP + r] (op)= bias[j] + sum_{k<Kd} W[k*ldw + j] * A[k*RP + r]      j < Nout (multiple of 4), r < 16
 // W is K-major in global memory (L2 resident), A / out are feature-major shared tiles.  mode: 0 store, 1 store+relu,
 // 2 accumulate into out.  All threads of the CTA must call; ends with __syncthreads().
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ W, int ldw, const float* __restrict__ bias,
-                                          const float* A, int Kd, float* out, int Nout, int mode, float* scratch) {
+// __noinline__: the kernels call it 5-6 times; one copy keeps the hot loop inside the instruction cache.
+__device__ __noinline__ void tile_gemm(const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                                       const float* A, int Kd, float* out, int Nout, int mode, float* scratch) {
     const int ntc = Nout >> 2, tiles = ntc * 4;
     int ksplit = 1;
     while (ksplit < 8 && tiles * ksplit * 2 <= NT && Kd >= ksplit * 16) ksplit *= 2;
@@ -129,43 +130,45 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ W, int ldw, 
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[c][r] = 0.f;
         if (active) {
-            // Weights stream from L2 (~250-cycle latency): register double buffering keeps KB 16-byte loads per
-            // thread in flight while the previous block of KB k-rows is consumed from registers.
+            // Weights stream from L2 (~250+ cycle latency).  Two register buffers of KB rows are filled and consumed
+            // in ping-pong (no register copies): KB 16-byte loads per thread are in flight while the other buffer
+            // feeds 16*KB FMAs.
             constexpr int KB = 8;
             const int k0 = ks * kchunk, k1 = min(Kd, k0 + kchunk);
             const float* wp = W + 4 * ct;
             const float* ap = A + 4 * rt;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 wn[KB];
+            auto load_block = [&](float4 (&w)[KB], int kb) {
 #pragma unroll
-            for (int i = 0; i < KB; ++i)
-                wn[i] = (k0 + i < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)(k0 + i) * ldw)) : zero4;
-            for (int kb = k0; kb < k1; kb += KB) {
-                float4 wc[KB];
-#pragma unroll
-                for (int i = 0; i < KB; ++i) wc[i] = wn[i];
-#pragma unroll
-                for (int i = 0; i < KB; ++i) {
-                    const int k = kb + KB + i;
-                    wn[i] = (k < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw)) : zero4;
-                }
-                float4 xa[KB];                                  // all shared loads of the block first (~30-cycle latency)
+                for (int i = 0; i < KB; ++i)
+                    w[i] = (kb + i < k1) ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)(kb + i) * ldw)) : zero4;
+            };
+            auto fma_block = [&](const float4 (&w)[KB], int kb) {
+                float4 xa[KB];                                  // all shared loads of the block first
 #pragma unroll
                 for (int i = 0; i < KB; ++i)
                     xa[i] = *reinterpret_cast<const float4*>(ap + min(kb + i, k1 - 1) * RP);   // rows past k1: zero weights
 #pragma unroll
                 for (int i = 0; i < KB; ++i) {
-                    const float4 w = wc[i];
+                    const float4 ww = w[i];
                     const float4 x = xa[i];
-                    acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
-                    acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
-                    acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
-                    acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
-                    acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
-                    acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
-                    acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
-                    acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+                    acc[0][0] = fmaf(ww.x, x.x, acc[0][0]); acc[0][1] = fmaf(ww.x, x.y, acc[0][1]);
+                    acc[0][2] = fmaf(ww.x, x.z, acc[0][2]); acc[0][3] = fmaf(ww.x, x.w, acc[0][3]);
+                    acc[1][0] = fmaf(ww.y, x.x, acc[1][0]); acc[1][1] = fmaf(ww.y, x.y, acc[1][1]);
+                    acc[1][2] = fmaf(ww.y, x.z, acc[1][2]); acc[1][3] = fmaf(ww.y, x.w, acc[1][3]);
+                    acc[2][0] = fmaf(ww.z, x.x, acc[2][0]); acc[2][1] = fmaf(ww.z, x.y, acc[2][1]);
+                    acc[2][2] = fmaf(ww.z, x.z, acc[2][2]); acc[2][3] = fmaf(ww.z, x.w, acc[2][3]);
+                    acc[3][0] = fmaf(ww.w, x.x, acc[3][0]); acc[3][1] = fmaf(ww.w, x.y, acc[3][1]);
+                    acc[3][2] = fmaf(ww.w, x.z, acc[3][2]); acc[3][3] = fmaf(ww.w, x.w, acc[3][3]);
                 }
+            };
+            float4 wa[KB], wb[KB];
+            load_block(wa, k0);
+            for (int kb = k0; kb < k1; kb += 2 * KB) {
+                load_block(wb, kb + KB);
+                fma_block(wa, kb);
+                load_block(wa, kb + 2 * KB);
+                if (kb + KB < k1) fma_block(wb, kb + KB);
             }
         }
         if (ksplit > 1) {                                   // tiles*ksplit <= NT here: single pass of the base loop
@@ -226,6 +229,7 @@ struct StepArgs {
     float* h_out; int64_t st_h;             // (T, N, H)   hidden state after each step
     float* q; int64_t st_q;                 // (T, N, A)
     int64_t* actions; int64_t st_act;       // (T, N) argmax, nullable
+    const float* eg_u; const int64_t* eg_a; const float* eg_eps;   // epsilon-greedy: action = u <= *eps ? a : argmax
     // saved for backward (nullable => inference)
     float* sv_xc;   // (T, N, Iih)  [x | c]   (PyTorch GRU input order)
     float* sv_vsq;  // (T, N, Vp)
@@ -267,7 +271,7 @@ __host__ __device__ inline SmemPlan make_smem(const StepDims& d, bool backward) 
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(NT) agent_step_fwd_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(NT, 1) agent_step_fwd_kernel(const StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     const StepDims d = a.d;
     const PackLayout L = make_layout(d);
@@ -355,7 +359,10 @@ __global__ void __launch_bounds__(NT) agent_step_fwd_kernel(const StepArgs a) {
             int best = 0;
             float bv = sQ[r];
             for (int c = 1; c < A; ++c) { const float v = sQ[c * RP + r]; if (v > bv) { bv = v; best = c; } }
-            a.actions[t * a.st_act + row0 + r] = best;
+            const int64_t ai = t * a.st_act + row0 + r;
+            int64_t act = best;
+            if (a.eg_u != nullptr && __ldg(a.eg_u + ai) <= __ldg(a.eg_eps)) act = __ldg(a.eg_a + ai);
+            a.actions[ai] = act;
         }
         if (training) {
             const int64_t n = a.N;
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(NT) agent_step_fwd_kernel(const StepArgs a) {
 //   [dx | dc] = dgi W_ih ; attention' (dc -> dvsq) ; dx += dvsq W_vsq[:, :H] (h is detached there) ;
 //   dpre = dx * 1[x > 0] ; d_xin = dpre W_aggr.
 // dgi / dgh / dvsq / dpre are stashed; the parameter gradients are batched GEMMs over the whole sequence afterwards.
-__global__ void __launch_bounds__(NT) agent_step_bwd_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(NT, 1) agent_step_bwd_kernel(const StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     const StepDims d = a.d;
     const PackLayout L = make_layout(d);
@@ -562,6 +569,16 @@ extern "C" UBS_API int ubs_agent_seq_fwd(int H, int M, int K, int A, int U, int 
                                          float* h_out, float* q, int64_t* actions,
                                          float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
                                          int64_t n_rows, int n_steps, void* stream) {
+    return ubs_agent_act_fwd(H, M, K, A, U, Fin, flags, packed, xin, h0, mask, h_out, q, actions, nullptr, nullptr,
+                             nullptr, sv_xc, sv_vsq, sv_alpha, sv_gate, n_rows, n_steps, stream);
+}
+
+extern "C" UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int Fin, int flags, const float* packed,
+                                         const float* xin, const float* h0, const uint32_t* mask,
+                                         float* h_out, float* q, int64_t* actions,
+                                         const float* eg_u, const int64_t* eg_a, const float* eg_eps,
+                                         float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
+                                         int64_t n_rows, int n_steps, void* stream) {
     ubs::StepArgs a{};
     a.d = ubs::mk_dims(H, M, K, A, U, Fin, flags);
     if (int rc = ubs::check_dims("ubs_agent_seq_fwd", a.d)) return rc;
@@ -573,6 +590,8 @@ extern "C" UBS_API int ubs_agent_seq_fwd(int H, int M, int K, int A, int U, int 
     if (n_rows == 0 || n_steps == 0) return 0;
     a.packed = packed; a.xin = xin; a.st_xin = n_rows * Fin; a.h0 = h0; a.mask = mask; a.st_mask = n_rows;
     a.h_out = h_out; a.st_h = n_rows * H; a.q = q; a.st_q = n_rows * A; a.actions = actions; a.st_act = n_rows;
+    a.eg_u = eg_u; a.eg_a = eg_a; a.eg_eps = eg_eps;
+    UBS_REQUIRE(eg_u == nullptr || (eg_a && eg_eps && actions), "ubs_agent_act_fwd: incomplete epsilon-greedy arguments");
     a.sv_xc = sv_xc; a.sv_vsq = sv_vsq; a.sv_alpha = sv_alpha; a.sv_gate = sv_gate; a.N = n_rows; a.T = n_steps;
     const int rpt = a.d.rows_per_tile();
     const unsigned grid = (unsigned)((n_rows + rpt - 1) / rpt);

@@ -77,7 +77,28 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
             rb = a.b_res ? a.b_res[ch] : 0.f;
         }
         wR[ch] = make_float4(r0, r1, rb, bs);
-        wD[ch] = make_float4(a.W_dst[ch * a.F_d], a.F_d > 1 ? a.W_dst[ch * a.F_d + 1] : 0.f, bs + bd, a.attn[ch]);
+        // leaky_relu(z) = (1+s)/2 z + (1-s)/2 |z|: the |z| part costs one FFMA per channel (free |.| operand
+        // modifier), the linear part folds into per-head constants (hP below)
+        wD[ch] = make_float4(a.W_dst[ch * a.F_d], a.F_d > 1 ? a.W_dst[ch * a.F_d + 1] : 0.f, bs + bd,
+                             0.5f * (1.0f - a.slope) * a.attn[ch]);
+    }
+    __syncthreads();
+    // hP[k] = (1+s)/2 * sum_d attn[k,d] * {W_src[k,d,0..3] | W_dst[k,d,0..1], b_src+b_dst}: 8 floats per head
+    float* hP = cbase + GPB * cstride;
+    if (tid < HEADS * 8) {
+        const int k = tid / 8, j = tid % 8;
+        float acc = 0.f;
+        for (int d0 = 0; d0 < D; ++d0) {
+            const int ch = k * D + d0;
+            const float at = a.attn[ch];
+            float w = 0.f;
+            if (j < 4) w = j == 0 ? wA[ch].x : j == 1 ? wA[ch].y : j == 2 ? wA[ch].z : wA[ch].w;
+            else if (j == 4) w = wD[ch].x;
+            else if (j == 5) w = wD[ch].y;
+            else if (j == 6) w = wD[ch].z;
+            acc = fmaf(at, w, acc);
+        }
+        hP[tid] = 0.5f * (1.0f + a.slope) * acc;
     }
     __syncthreads();
 
@@ -112,6 +133,9 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
             cbuf[ch] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
         }
         __syncwarp();
+        float lin[HEADS];
+#pragma unroll
+        for (int k = 0; k < HEADS; ++k) lin[k] = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
 
         float m[HEADS], l[HEADS], acc[HEADS][FS];
 #pragma unroll
@@ -128,7 +152,13 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
             for (int k = 0; k < HEADS; ++k) {
                 const float4* wk = wA + k * D;
                 const float2* ck = cbuf + k * D;
-                float s = 0.f;
+                // linear part of the score: (1+s)/2 * attn_k . (W_src x + W_dst x_v + b)
+                const float4 pk = *reinterpret_cast<const float4*>(hP + k * 8);
+                float s = lin[k];
+                s = fmaf(pk.x, x[0], s);
+                if constexpr (FS > 1) s = fmaf(pk.y, x[1], s);
+                if constexpr (FS > 2) s = fmaf(pk.z, x[2], s);
+                if constexpr (FS > 3) s = fmaf(pk.w, x[3], s);
 #pragma unroll 8
                 for (int d = 0; d < D; ++d) {
                     const float4 w = wk[d];
@@ -138,12 +168,11 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
                     if constexpr (FS > 1) z = fmaf(w.y, x[1], z);
                     if constexpr (FS > 2) z = fmaf(w.z, x[2], z);
                     if constexpr (FS > 3) z = fmaf(w.w, x[3], z);
-                    const float y = fmaxf(z, slope * z);        // leaky_relu for 0 <= slope <= 1
-                    s = fmaf(c.y, y, s);
+                    s = fmaf(c.y, fabsf(z), s);                 // (1-s)/2 * attn * |z|
                 }
                 const float mn = fmaxf(m[k], s);
-                const float sc = expf(m[k] - mn);
-                const float p = expf(s - mn);
+                const float sc = __expf(m[k] - mn);
+                const float p = __expf(s - mn);
                 l[k] = fmaf(l[k], sc, p);
 #pragma unroll
                 for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[f]);
@@ -154,7 +183,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
 #pragma unroll
         for (int k = 0; k < HEADS; ++k) {
             const float M = group_max<GS>(m[k]);
-            const float sc = (m[k] == -CUDART_INF_F) ? 0.f : expf(m[k] - M);
+            const float sc = (m[k] == -CUDART_INF_F) ? 0.f : __expf(m[k] - M);
             l[k] = group_sum<GS>(l[k] * sc);
 #pragma unroll
             for (int f = 0; f < FS; ++f) acc[k][f] = group_sum<GS>(acc[k][f] * sc);
@@ -417,20 +446,18 @@ static int bwd_grid(int64_t n_dst) {
 template <int FS, int HEADS>
 static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
     const int H = HEADS * a.D;
-    const bool small = n_edges <= 12 * (int64_t)a.n_dst;           // mean in-degree <= 12: 8 lanes per destination
-    const int gs = small ? 8 : 32;
+    // lanes per destination from the mean in-degree: 8 (<= 12 edges), 16 (<= 96: deg 80 = 5 full passes), else 32
+    const int64_t nd = a.n_dst > 0 ? a.n_dst : 1;
+    int gs = n_edges <= 12 * nd ? 8 : (n_edges <= 96 * nd ? 16 : 32);
+    while (gs < 32 && nd * gs / 32 < (int64_t)kNumSMs * 8) gs *= 2;   // small launches (act step): parallelism first
     const int gpb = 256 / gs;
     int64_t need = ((int64_t)a.n_dst + gpb - 1) / gpb;
-    int64_t cap = (int64_t)kNumSMs * 8;
+    int64_t cap = (int64_t)kNumSMs * 4;                            // persistent: 4 resident CTAs per SM (64 regs)
     const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
-    const size_t smem = (size_t)H * 3 * sizeof(float4) + (size_t)gpb * (2 * H + 2) * sizeof(float);
-    if (small) {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(gatv2_fwd_kernel<FS, HEADS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gatv2_fwd_kernel<FS, HEADS, 8><<<grid, 256, smem, st>>>(a);
-    } else {
-        gatv2_fwd_kernel<FS, HEADS, 32><<<grid, 256, smem, st>>>(a);
-    }
+    const size_t smem = (size_t)H * 3 * sizeof(float4) + (size_t)gpb * (2 * H + 2) * sizeof(float) + HEADS * 8 * sizeof(float);
+    if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8><<<grid, 256, smem, st>>>(a);
+    else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16><<<grid, 256, smem, st>>>(a);
+    else gatv2_fwd_kernel<FS, HEADS, 32><<<grid, 256, smem, st>>>(a);
     return check_launch("ubs_gatv2_fwd");
 }
 

@@ -246,16 +246,15 @@ class MultiAgentQLearner:
         else:
             arena.h[0].copy_(h0)
         if not hasattr(arena, "explore_u"):          # fixed addresses: captured act graphs read these buffers
-            arena.explore_u = th.empty(arena.S, self.n_envs, device=self.device)
+            arena.explore_u = th.empty(arena.S, arena.layout.N, device=self.device)
             arena.explore_a = th.empty(arena.S, arena.layout.N, dtype=th.int64, device=self.device)
-        arena.explore_u.uniform_()
+        u = th.rand(arena.S, self.n_envs, 1, device=self.device)
+        arena.explore_u.copy_(u.expand(-1, -1, self.n_agents).reshape(arena.S, -1))
         arena.explore_a.random_(0, self.n_actions)
 
     def _act_arena_eager(self, arena, t):
-        q = self.policy_net.arena_step(arena, t)
-        explore = (arena.explore_u[t] <= self._eps_dev).repeat_interleave(self.n_agents)
-        arena.acts[t].copy_(th.where(explore, arena.explore_a[t], arena.acts[t]))
-        return q
+        # ε-greedy is fused into the step kernel: one uniform per env (explore_u holds it repeated for the env's agents)
+        return self.policy_net.arena_step(arena, t, explore=(arena.explore_u[t], arena.explore_a[t], self._eps_dev))
 
     def act_arena(self, arena, t, eps_thres):
         """``act`` on arena slot t (observation already staged with ``arena.load``): writes ``arena.h[t+1]`` and the

@@ -140,6 +140,60 @@ class GATv2Fused(th.autograd.Function):
                 gbr if b_res is not None else None, None, None, None, None)
 
 
+def gat_aggregate_supported(heads: int, D: int, slope: float) -> bool:
+    H = heads * D
+    return H in (32, 64, 128, 256) and heads in (1, 2, 4, 8) and D % (H // 32) == 0 and 0.0 <= slope <= 1.0
+
+
+class GATAggregate(th.autograd.Function):
+    """GATv2 attention + aggregation on pre-projected features over a general CSR (``ubs_gat_aggr_fwd/bwd``).
+    ``forward(el (n_src,H), er (n_dst,H), res (n_dst,H)|None, indptr, src_idx|None, attn, heads, D, slope, flags)``."""
+
+    @staticmethod
+    def forward(ctx, el, er, res, indptr, src_idx, attn, heads, D, slope, flags):
+        _lib.require_cuda(el, er, indptr, attn)
+        lib = _lib.load()
+        el, er, res, attn_c = _f32c(el), _f32c(er), _f32c(res), _f32c(attn)
+        if indptr.dtype != th.int32 or (src_idx is not None and src_idx.dtype != th.int32):
+            raise TypeError("indptr / src_idx must be int32")
+        n_dst, H = er.shape[0], heads * D
+        n_edges = el.shape[0] if src_idx is None else src_idx.shape[0]
+        need = any(t is not None and t.requires_grad for t in (el, er, res, attn))
+        out = th.empty(n_dst, H, dtype=th.float32, device=er.device)
+        smax = th.empty(n_dst, heads, dtype=th.float32, device=er.device) if need else None
+        ssum = th.empty_like(smax) if need else None
+        P = _lib.ptr
+        with _timed("gat_aggr_fwd", (n_dst, n_edges, H, heads, need)):
+            _lib.check(lib.ubs_gat_aggr_fwd(P(el), P(er), P(res), P(indptr), P(src_idx), P(attn_c), P(out), P(smax),
+                                            P(ssum), n_dst, n_edges, heads, D, float(slope), int(flags), _lib.stream()),
+                       "ubs_gat_aggr_fwd")
+        if need:
+            ctx.save_for_backward(el, er, res, indptr, src_idx, attn_c, out, smax, ssum)
+            ctx.cfg = (heads, D, float(slope), int(flags), n_edges, attn.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        el, er, res, indptr, src_idx, attn, out, smax, ssum = ctx.saved_tensors
+        heads, D, slope, flags, n_edges, attn_shape = ctx.cfg
+        lib = _lib.load()
+        n_dst, H = er.shape[0], heads * D
+        grad_out = _f32c(grad_out)
+        g_el = (th.zeros_like if src_idx is not None else th.empty_like)(el)
+        if src_idx is None and el.shape[0] != n_edges:
+            g_el.zero_()
+        g_er = th.empty_like(er)
+        g_res = th.empty_like(er) if res is not None else None
+        g_attn = th.empty(H, dtype=th.float32, device=er.device)
+        ws = th.empty(int(lib.ubs_gat_aggr_bwd_workspace(n_dst, heads, D)), dtype=th.float32, device=er.device)
+        P = _lib.ptr
+        with _timed("gat_aggr_bwd", (n_dst, n_edges, H, heads, True)):
+            _lib.check(lib.ubs_gat_aggr_bwd(P(el), P(er), P(res), P(indptr), P(src_idx), P(attn), P(out), P(grad_out),
+                                            P(smax), P(ssum), P(g_el), P(g_er), P(g_res), P(g_attn), P(ws), n_dst,
+                                            n_edges, heads, D, slope, flags, _lib.stream()), "ubs_gat_aggr_bwd")
+        return g_el, g_er, g_res, None, None, g_attn.view(attn_shape), None, None, None, None
+
+
 class BlockAttention(th.autograd.Function):
     """TarMAC attention over a block-diagonal comm graph.  ``vsq`` is ``(N, M + 2K)`` laid out ``[v | s | q]``."""
 
@@ -258,7 +312,8 @@ def agent_pack(dims: AgentDims, params: dict, out=None):
     return out
 
 
-def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False, h_out=None, q=None, acts=None):
+def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False, h_out=None, q=None, acts=None,
+                    explore=None):
     """Inference: ``xin (T,N,Fin)``, ``h0 (N,H)`` -> ``q (T,N,A)``, ``h_out (T,N,H)`` [, greedy actions (T,N) int64].
     ``h_out`` / ``q`` / ``acts`` may be preallocated contiguous destinations (e.g. slices of a sequence arena)."""
     lib = _lib.load()
@@ -275,10 +330,12 @@ def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False, 
         if t_ is not None and (not t_.is_contiguous() or t_.numel() != n_):
             raise ValueError("agent_seq_infer: output buffers must be contiguous and exactly sized")
     want_actions = acts is not None
+    eg_u, eg_a, eg_eps = explore if explore is not None else (None, None, None)      # fused epsilon-greedy
     with _timed("agent_seq_fwd", (T, N, dims.ints(), False)):
-        _lib.check(lib.ubs_agent_seq_fwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(xin), _lib.ptr(h0), _lib.ptr(mask),
-                                         _lib.ptr(h_out), _lib.ptr(q), _lib.ptr(acts), None, None, None, None,
-                                         N, T, _lib.stream()), "ubs_agent_seq_fwd")
+        _lib.check(lib.ubs_agent_act_fwd(*dims.ints(), _lib.ptr(packed), _lib.ptr(xin), _lib.ptr(h0), _lib.ptr(mask),
+                                         _lib.ptr(h_out), _lib.ptr(q), _lib.ptr(acts), _lib.ptr(eg_u), _lib.ptr(eg_a),
+                                         _lib.ptr(eg_eps), None, None, None, None, N, T, _lib.stream()),
+                   "ubs_agent_act_fwd")
     return (q, h_out, acts) if want_actions else (q, h_out)
 
 
@@ -361,6 +418,24 @@ class AgentSequence(th.autograd.Function):
 # ====================================================================================================================
 # Strided-segment relation encoder (ubs_gatv2_seg_fwd / ubs_gatv2_seg_bwd): all timesteps of an arena in one launch per
 # relation, every relation writing its own column block of ONE (rows, R*H) output buffer.
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, i):
+    key = (dev.index, i)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = th.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class RelSpec:
     """One relation of a strided-segment encode: raw device addresses + strides (elements) + feature widths."""
 
@@ -386,15 +461,24 @@ class SegmentEncode(th.autograd.Function):
         out = th.empty(rows, R * H, dtype=th.float32, device=dev)
         stats = th.empty(R, 2, rows, heads, dtype=th.float32, device=dev) if need_grad else None
         ps = [_f32c(p.detach()) if p is not None else None for p in params]
+        # small launches (the act step) cannot fill the chip: relations run side by side on a forked stream
+        fork = R > 1 and rows <= 8192 and TIMER is None
+        cur = th.cuda.current_stream()
         for r, sp in enumerate(specs):
             W = ps[7 * r:7 * r + 7]
-            with _timed("gatv2_fwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, need_grad)):
+            side = _side_stream(dev, r) if (fork and r > 0) else None
+            if side is not None:
+                side.wait_stream(cur)
+            with _timed("gatv2_fwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, need_grad)), \
+                    (th.cuda.stream(side) if side is not None else _nullctx()):
                 _lib.check(lib.ubs_gatv2_seg_fwd(
                     sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
                     out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]) if need_grad else None,
                     _lib.ptr(stats[r, 1]) if need_grad else None, n_seg, n_dst_seg, sp.n_edges_hint, sp.st_xsrc, st_xdst,
                     sp.st_ip, sp.st_sidx, R * H, sp.F_s, F_d, heads, D, float(slope), int(flags), _lib.stream()),
                     "ubs_gatv2_seg_fwd")
+            if side is not None:
+                cur.wait_stream(side)
         if need_grad:
             ctx.save_for_backward(keepalive, out, stats, *[p for p in ps if p is not None])
             ctx.cfg = (specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, float(slope), int(flags),
@@ -443,117 +527,151 @@ def seq2_supported(dims: AgentDims) -> bool:
     return max(int(lib.ubs_agent_seq2_smem_bytes(dims.H, dims.M, dims.K, dims.U, dims.flags, b)) for b in (0, 1)) <= 227 * 1024
 
 
-def _vsq_weights(params, dims):
-    """Concatenated ``[W_val; W_sign; W_que]`` (Vp, 2H) and bias (Vp), zero padded to a multiple of 4 rows."""
-    w = th.cat((params["W_val"], params["W_sign"], params["W_que"]), 0)
-    b = th.cat((params["b_val"], params["b_sign"], params["b_que"]), 0)
-    if dims.Vp != dims.V:
-        w = th.cat((w, w.new_zeros(dims.Vp - dims.V, w.shape[1])), 0)
-        b = th.cat((b, b.new_zeros(dims.Vp - dims.V)), 0)
-    return w, b
+class Seq2Weights:
+    """Derived weight tensors of the resident-weight sequence path, rebuilt only when a parameter changes:
+    ``Wx (Vp+3H, H)`` = ``[W_vsq[:, :H]; W_ih[:, :H]]`` and its bias (ONE observation-side GEMM gives ``[pv | pg]``),
+    the K-major recurrent blocks the forward kernel keeps in shared memory, and the original-layout blocks of the
+    backward kernel."""
+
+    def __init__(self, dims, params):
+        H, M, K = dims.H, dims.M, dims.K
+        p = {k: (None if v is None else v.detach()) for k, v in params.items()}
+        W_ih, W_hh = p["W_ih"], p["W_hh"]
+        self.b_hh = p["b_hh"].contiguous()
+        self.wt_hh = W_hh.t().contiguous()                       # (H, 3H)
+        self.w_hh = W_hh.contiguous()                            # (3H, H)
+        if dims.tarmac:
+            Wv = th.cat((p["W_val"], p["W_sign"], p["W_que"]), 0)
+            bv = th.cat((p["b_val"], p["b_sign"], p["b_que"]), 0)
+            if dims.Vp != dims.V:
+                Wv = th.cat((Wv, Wv.new_zeros(dims.Vp - dims.V, Wv.shape[1])), 0)
+                bv = th.cat((bv, bv.new_zeros(dims.Vp - dims.V)), 0)
+            self.Wx = th.cat((Wv[:, :H], W_ih[:, :H]), 0).contiguous()          # (Vp + 3H, H)
+            self.bx = th.cat((bv, p["b_ih"]), 0)
+            self.wt_vsq_h = Wv[:, H:].t().contiguous()           # (H, Vp)
+            self.wt_ih_c = W_ih[:, H:].t().contiguous()          # (M, 3H)
+            self.w_ih_c = W_ih[:, H:].contiguous()               # (3H, M)
+            # dx = [dgi | dv] @ [W_ih[:, :H]; W_vsq[:, :H]]
+            self.Wdx = th.cat((W_ih[:, :H], Wv[:, :H]), 0).contiguous()         # (3H + Vp, H)
+        else:
+            self.Wx, self.bx = W_ih[:, :H].contiguous(), p["b_ih"]
+            self.wt_vsq_h = self.wt_ih_c = self.w_ih_c = None
+            self.Wdx = self.Wx
+        self.W_aggr, self.b_aggr = p["W_aggr"], p["b_aggr"]
+        self.W_out, self.b_out = p["W_out"], p["b_out"]
 
 
-def _seq2_forward(dims, params, xg, h0, mask, training):
+_SEQ2_CACHE = {}
+
+
+def seq2_weights(dims, params) -> Seq2Weights:
+    key = tuple((t.data_ptr(), t._version) for t in params.values() if t is not None)
+    slot = (dims.ints(), key[0][0])
+    hit = _SEQ2_CACHE.get(slot)
+    if hit is None or hit[0] != key:
+        if len(_SEQ2_CACHE) > 16:
+            _SEQ2_CACHE.clear()
+        hit = (key, Seq2Weights(dims, params))
+        _SEQ2_CACHE[slot] = hit
+    return hit[1]
+
+
+def _seq2_forward(dims, W: Seq2Weights, xg, h0, mask, training):
     lib = _lib.load()
     T, N = xg.shape[0], xg.shape[1]
     TN, H, M, K, U, Vp = T * N, dims.H, dims.M, dims.K, dims.U, dims.Vp
     f32 = dict(dtype=th.float32, device=xg.device)
     xg2 = xg.reshape(TN, dims.Fin)
-    x = th.relu_(th.addmm(params["b_aggr"], xg2, params["W_aggr"].t())) if dims.aggr else xg2
-    W_ih, W_hh = params["W_ih"], params["W_hh"]
-    pg = th.addmm(params["b_ih"], x, W_ih[:, :H].t())
-    wt_hh = W_hh.t().contiguous()
-    Wv = pv = wt_vsq_h = wt_ih_c = None
-    if dims.tarmac:
-        Wv, bv = _vsq_weights(params, dims)
-        pv = th.addmm(bv, x, Wv[:, :H].t())
-        wt_vsq_h = Wv[:, H:].t().contiguous()
-        wt_ih_c = W_ih[:, H:].t().contiguous()
+    x = th.relu_(th.addmm(W.b_aggr, xg2, W.W_aggr.t())) if dims.aggr else xg2
+    pvg = th.addmm(W.bx, x, W.Wx.t())                              # (TN, Vp + 3H) = [pv | pg], one GEMM
+    ld = pvg.shape[1]
     h_out = th.empty(T, N, H, **f32)
     sv_gate = th.empty(T, N, 4 * H, **f32) if training else None
     sv_vsq = th.empty(T, N, Vp, **f32) if training and dims.tarmac else None
     sv_alpha = th.empty(T, N, U, **f32) if training and dims.tarmac else None
     sv_c = th.empty(T, N, M, **f32) if training and dims.tarmac else None
     P = _lib.ptr
+    pv_ptr = pvg.data_ptr() if dims.tarmac else None
+    pg_ptr = pvg.data_ptr() + 4 * (Vp if dims.tarmac else 0)
     with _timed("agent_seq2_fwd", (T, N, dims.ints(), training)):
-        _lib.check(lib.ubs_agent_seq2_fwd(H, M, K, U, dims.flags, P(wt_vsq_h), P(wt_ih_c), P(wt_hh), P(params["b_hh"]),
-                                          P(pv), P(pg), P(h0), P(mask), P(h_out), P(sv_vsq), P(sv_alpha), P(sv_c),
-                                          P(sv_gate), N, T, _lib.stream()), "ubs_agent_seq2_fwd")
-    q = th.addmm(params["b_out"], h_out.view(TN, H), params["W_out"].t()).view(T, N, dims.A)
-    return q, h_out, (x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate)
+        _lib.check(lib.ubs_agent_seq2_fwd(H, M, K, U, dims.flags, P(W.wt_vsq_h), P(W.wt_ih_c), P(W.wt_hh), P(W.b_hh),
+                                          pv_ptr, pg_ptr, P(h0), P(mask), P(h_out), P(sv_vsq), P(sv_alpha), P(sv_c),
+                                          P(sv_gate), ld, ld, N, T, _lib.stream()), "ubs_agent_seq2_fwd")
+    q = th.addmm(W.b_out, h_out.view(TN, H), W.W_out.t()).view(T, N, dims.A)
+    return q, h_out, (x, sv_vsq, sv_alpha, sv_c, sv_gate)
 
 
 def agent_seq2_infer(dims: AgentDims, params: dict, xg, h0, mask):
     """Inference through the resident-weight sequence kernel: returns ``q (T,N,A)``, ``h_out (T,N,H)``."""
     _lib.require_cuda(xg, h0)
-    p = {k: (None if v is None else v.detach()) for k, v in params.items()}
-    q, h_out, _ = _seq2_forward(dims, p, _f32c(xg), _f32c(h0), mask, False)
+    q, h_out, _ = _seq2_forward(dims, seq2_weights(dims, params), _f32c(xg), _f32c(h0), mask, False)
     return q, h_out
 
 
 class AgentSequence2(th.autograd.Function):
     """Same contract as :class:`AgentSequence` (``forward(xg, h0, mask, dims, *params[PARAM_ORDER])`` ->
-    ``(q, h_last, h_all)``) on the resident-weight kernels."""
+    ``(q, h_last, h_all)``) on the resident-weight kernels.  All parameter gradients come from a handful of batched
+    GEMMs over the T*N rows: the backward kernel writes ONE stash ``[dgi | dvsq | dgh]`` whose column blocks feed
+    ``dx``, ``[dW_ih_x; dW_vsq_x]``, ``[dW_vsq_h; dW_hh]`` and all bias gradients without copies."""
 
     @staticmethod
     def forward(ctx, xg, h0, mask, dims, *params):
         _lib.require_cuda(xg, h0)
         xg, h0 = _f32c(xg), _f32c(h0)
-        p = {k: (None if v is None else _f32c(v.detach())) for k, v in zip(PARAM_ORDER, params)}
-        q, h_out, (x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate) = _seq2_forward(dims, p, xg, h0, mask, True)
-        ctx.dims = dims
+        W = seq2_weights(dims, dict(zip(PARAM_ORDER, params)))
+        q, h_out, (x, sv_vsq, sv_alpha, sv_c, sv_gate) = _seq2_forward(dims, W, xg, h0, mask, True)
+        ctx.dims, ctx.W = dims, W
         ctx.has = [v is not None for v in params]
-        ctx.save_for_backward(xg, h0, h_out, x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate, *[v for v in p.values() if v is not None])
+        ctx.save_for_backward(xg, h0, h_out, x, sv_vsq, sv_alpha, sv_c, sv_gate)
         ctx.mark_non_differentiable(h_out)
         return q, h_out[-1].clone(), h_out
 
     @staticmethod
     def backward(ctx, dq, dh_last, _dh_all):
-        xg, h0, h_out, x, Wv, sv_vsq, sv_alpha, sv_c, sv_gate, *plist = ctx.saved_tensors
-        dims = ctx.dims
-        it = iter(plist)
-        p = {k: (next(it) if has else None) for k, has in zip(PARAM_ORDER, ctx.has)}
+        xg, h0, h_out, x, sv_vsq, sv_alpha, sv_c, sv_gate = ctx.saved_tensors
+        dims, W = ctx.dims, ctx.W
         lib = _lib.load()
         T, N = xg.shape[0], xg.shape[1]
         TN, H, M, K, U, A, V, Vp = T * N, dims.H, dims.M, dims.K, dims.U, dims.A, dims.V, dims.Vp
+        H3 = 3 * H
         f32 = dict(dtype=th.float32, device=xg.device)
         dq2 = (_f32c(dq) if dq is not None else th.zeros(T, N, A, **f32)).view(TN, A)
-        dhq = (dq2 @ p["W_out"]).view(T, N, H)
+        dhq = (dq2 @ W.W_out).view(T, N, H)
         if dh_last is not None:
             dhq[T - 1] += dh_last
-        W_ih, W_hh = p["W_ih"], p["W_hh"]
-        w_ih_c = W_ih[:, H:].contiguous() if dims.tarmac else None
-        st_dgi, st_dgh = th.empty(T, N, 3 * H, **f32), th.empty(T, N, 3 * H, **f32)
-        st_dvsq = th.empty(T, N, Vp, **f32) if dims.tarmac else None
+        ldS = H3 + Vp + H3                                         # [dgi | dvsq | dgh]
+        S = th.empty(TN, ldS, **f32)
         d_h0 = th.empty_like(h0) if ctx.needs_input_grad[1] else None
         P = _lib.ptr
+        sp = S.data_ptr()
         with _timed("agent_seq2_bwd", (T, N, dims.ints(), True)):
-            _lib.check(lib.ubs_agent_seq2_bwd(H, M, K, U, dims.flags, P(W_hh), P(w_ih_c), P(h0), P(h_out), P(sv_vsq),
-                                              P(sv_alpha), P(sv_gate), P(dhq), P(st_dgi), P(st_dgh), P(st_dvsq),
-                                              P(d_h0), N, T, _lib.stream()), "ubs_agent_seq2_bwd")
-        dgi, dgh = st_dgi.view(TN, 3 * H), st_dgh.view(TN, 3 * H)
+            _lib.check(lib.ubs_agent_seq2_bwd(H, M, K, U, dims.flags, P(W.w_hh), P(W.w_ih_c), P(h0), P(h_out), P(sv_vsq),
+                                              P(sv_alpha), P(sv_gate), P(dhq), sp, sp + 4 * (H3 + Vp),
+                                              sp + 4 * H3 if dims.tarmac else None, P(d_h0), ldS, N, T, _lib.stream()),
+                       "ubs_agent_seq2_bwd")
         hprev = th.cat((h0.unsqueeze(0), h_out[:-1]), 0).view(TN, H)
-        g = {}
+        Sx, Sh = S[:, :H3 + Vp], S[:, H3:]                          # [dgi | dvsq] and [dvsq | dgh]
+        gb = S.sum(0)
+        g = {"b_ih": gb[:H3], "b_hh": gb[H3 + Vp:]}
         g["W_out"], g["b_out"] = dq2.t() @ h_out.view(TN, H), dq2.sum(0)
-        g["W_hh"], g["b_hh"] = dgh.t() @ hprev, dgh.sum(0)
-        g["b_ih"] = dgi.sum(0)
-        dx = dgi @ W_ih[:, :H]
+        Gx = Sx.t() @ x                                             # (3H + Vp, H): [dW_ih[:, :H]; dW_vsq[:, :H]]
+        Gh = Sh.t() @ hprev                                         # (Vp + 3H, H): [dW_vsq[:, H:]; dW_hh]
+        g["W_hh"] = Gh[Vp:]
+        dx = Sx @ W.Wdx                                             # (TN, H)
         if dims.tarmac:
-            dv = st_dvsq.view(TN, Vp)
-            g["W_ih"] = th.cat((dgi.t() @ x, dgi.t() @ sv_c.view(TN, M)), 1)
-            gw = th.cat((dv.t() @ x, dv.t() @ hprev), 1)
-            gb = dv.sum(0)
-            g["W_val"], g["b_val"] = gw[:M], gb[:M]
-            g["W_sign"], g["b_sign"] = gw[M:M + K], gb[M:M + K]
-            g["W_que"], g["b_que"] = gw[M + K:V], gb[M + K:V]
-            dx.addmm_(dv, Wv[:, :H])
+            g["W_ih"] = th.cat((Gx[:H3], S[:, :H3].t() @ sv_c.view(TN, M)), 1)
+            gw = th.cat((Gx[H3:], Gh[:Vp]), 1)                      # (Vp, 2H)
+            gbv = gb[H3:H3 + Vp]
+            g["W_val"], g["b_val"] = gw[:M], gbv[:M]
+            g["W_sign"], g["b_sign"] = gw[M:M + K], gbv[M:M + K]
+            g["W_que"], g["b_que"] = gw[M + K:V], gbv[M + K:V]
         else:
-            g["W_ih"] = dgi.t() @ x
+            g["W_ih"] = Gx[:H3]
         if dims.aggr:
             dpre = dx.mul_(x > 0)
             xg2 = xg.view(TN, dims.Fin)
             g["W_aggr"], g["b_aggr"] = dpre.t() @ xg2, dpre.sum(0)
-            d_xg = (dpre @ p["W_aggr"]).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
+            d_xg = (dpre @ W.W_aggr).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         else:
             d_xg = dx.view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         grads = tuple(g.get(k) if has else None for k, has in zip(PARAM_ORDER, ctx.has))

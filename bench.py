@@ -243,9 +243,8 @@ def run_ours(a):
         for _ in range(warmup):
             fn()
         if sampler:
-            t_w = time.perf_counter()
-            while time.perf_counter() - t_w < 0.6:   # make sure the sampler is alive; keep the GPU under the same load
-                fn()
+            for _ in range(40):                 # ~0.5 s under the same load so that nvidia-smi is sampling by now
+                fn()                            # (a FIXED count: every rank must issue the same number of collectives)
         barrier()
         _lib.reset_launch_count()
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
@@ -279,12 +278,13 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel: CUDA events around every C-ABI call during one extra step
     roofline = None
+    if use_arena:
+        learner.args.cuda_graphs = False                 # replayed graphs bypass the Python-side event hooks
     if rank == 0:
-        if use_arena:
-            learner.args.cuda_graphs = False             # replayed graphs bypass the Python-side event hooks
         ops.TIMER = ops.KernelTimer()
-        value_step()
-        th.cuda.synchronize()
+    value_step()                                         # every rank runs it: the update contains the all-reduce
+    th.cuda.synchronize()
+    if rank == 0:
         recs = [(n, m, s_.elapsed_time(e_)) for n, m, s_, e_ in ops.TIMER.records]
         ops.TIMER = None
         groups, by_name = {}, {}

@@ -115,6 +115,14 @@ UBS_API int ubs_gat_aggr_bwd(const float* el, const float* er, const float* res,
                      float* grad_attn, float* workspace, int64_t n_dst, int64_t n_edges, int heads, int D,
                      float negative_slope, int flags, void* stream);
 
+/* ---- Dense projection on the tensor cores: C[M,N] = act(A[M,K] W[N,K]^T + bias), fp32 in/out, 3xTF32 -----------
+ * tcgen05.mma.kind::tf32 with TMEM accumulators; every operand is split hi + lo (13 low mantissa bits) and
+ * hi*hi + hi*lo + lo*hi is accumulated in fp32, so the result is fp32-accurate (~2^-21) — single-pass TF32 would
+ * break the 1e-5 parity bar.  A, W row-major (nn.Linear layout), K % 32 == 0, N % 16 == 0, N <= 256, 16-byte aligned
+ * rows.  Returns 3 if W does not fit shared memory.  relu != 0 applies ReLU in the epilogue.                        */
+UBS_API int ubs_tf32x3_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                    float* C, int64_t ldc, int64_t M, int N, int K, int relu, void* stream);
+
 /* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
  * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
  * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.

@@ -527,6 +527,30 @@ def seq2_supported(dims: AgentDims) -> bool:
     return max(int(lib.ubs_agent_seq2_smem_bytes(dims.H, dims.M, dims.K, dims.U, dims.flags, b)) for b in (0, 1)) <= 227 * 1024
 
 
+def tc_linear_supported(K: int, N: int) -> bool:
+    return K % 32 == 0 and K >= 32 and N % 16 == 0 and 16 <= N <= 256 and 2 * (K // 32) * N * 128 + 2 * 32768 + 2048 <= 227 * 1024
+
+
+def tc_linear(x, w, bias=None, relu=False, out=None):
+    """``act(x @ w.T + bias)`` on the tensor cores with 3xTF32 (``ubs_tf32x3_gemm``): fp32-accurate.  ``x (M,K)`` and
+    ``w (N,K)`` may be row-strided views (last dim contiguous, 16-byte aligned rows); no autograd."""
+    lib = _lib.load()
+    _lib.require_cuda(x, w)
+    M, K = x.shape
+    N = w.shape[0]
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    if out is None:
+        out = th.empty(M, N, dtype=th.float32, device=x.device)
+    with _timed("tf32x3_gemm", (M, N, K)):
+        _lib.check(lib.ubs_tf32x3_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(bias),
+                                       out.data_ptr(), out.stride(0), M, N, K, int(relu), _lib.stream()),
+                   "ubs_tf32x3_gemm")
+    return out
+
+
 class Seq2Weights:
     """Derived weight tensors of the resident-weight sequence path, rebuilt only when a parameter changes:
     ``Wx (Vp+3H, H)`` = ``[W_vsq[:, :H]; W_ih[:, :H]]`` and its bias (ONE observation-side GEMM gives ``[pv | pg]``),

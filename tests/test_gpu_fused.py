@@ -49,6 +49,7 @@ CASES = [
     ("tarmac", 128, 8, 10, 4, "realistic", 0.8, None),    # H=128 (scaled)
     (None, 64, 8, 30, 5, "realistic", 1.0, None),         # independent agents: plain GRU
     ("tarmac", 64, 8, 0, 6, "full", 0.7, 423),            # exp2: MLP observation encoder + TarMAC
+    ("tarmac", 64, 8, 12, 16, "realistic", 0.8, None),    # T*N = 512 rows: window projections run on tcgen05 (3xTF32)
 ]
 
 
@@ -107,6 +108,7 @@ def test_forward_sequence_bptt_matches_oracle(c, H, U, Gn, B, profile, comm_p, f
     ops.TIMER = None
     if use_seq2 and H <= 64:
         assert "agent_seq2_fwd" in used and "agent_seq2_bwd" in used, "resident-weight kernels must be the path that ran"
+        assert ("tf32x3_gemm" in used) == (T * B * U >= 512), "tensor-core projections for windows of >= 512 rows"
     else:
         assert "agent_seq_fwd" in used and "agent_seq_bwd" in used
     assert_close(q_d, outs["r32"][0], rtol=3e-5, atol_scale=1e-5, what="q sequence")

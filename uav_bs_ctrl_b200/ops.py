@@ -551,6 +551,29 @@ def tc_linear(x, w, bias=None, relu=False, out=None):
     return out
 
 
+USE_TC = True       # batched observation-side projections on the tensor cores (3xTF32); False: cuBLAS fp32
+
+
+def dense(x, w, bias=None, relu=False):
+    """``act(x @ w.T + bias)`` for the batched (T*N-row) projections: the tcgen05 3xTF32 kernel when the shape fits
+    (wide outputs are split into column blocks), else the fp32 library GEMM.  No autograd."""
+    M, K = x.shape
+    N = w.shape[0]
+    if USE_TC and x.is_cuda and M >= 512:
+        blocks = None
+        if tc_linear_supported(K, N):
+            blocks = [(0, N)]
+        elif N % 32 == 0 and tc_linear_supported(K, N // 2):
+            blocks = [(0, N // 2), (N // 2, N)]
+        if blocks is not None and x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0 and x.stride(1) == 1 and w.is_contiguous():
+            out = th.empty(M, N, dtype=th.float32, device=x.device)
+            for lo, hi in blocks:
+                tc_linear(x, w[lo:hi], None if bias is None else bias[lo:hi], relu=relu, out=out[:, lo:hi])
+            return out
+    out = th.addmm(bias, x, w.t()) if bias is not None else x @ w.t()
+    return th.relu_(out) if relu else out
+
+
 class Seq2Weights:
     """Derived weight tensors of the resident-weight sequence path, rebuilt only when a parameter changes:
     ``Wx (Vp+3H, H)`` = ``[W_vsq[:, :H]; W_ih[:, :H]]`` and its bias (ONE observation-side GEMM gives ``[pv | pg]``),
@@ -581,7 +604,9 @@ class Seq2Weights:
             self.Wx, self.bx = W_ih[:, :H].contiguous(), p["b_ih"]
             self.wt_vsq_h = self.wt_ih_c = self.w_ih_c = None
             self.Wdx = self.Wx
+        self.Wdx_t = self.Wdx.t().contiguous()                   # (H, 3H + Vp): nn.Linear layout of the dx projection
         self.W_aggr, self.b_aggr = p["W_aggr"], p["b_aggr"]
+        self.W_aggr_t = None if p["W_aggr"] is None else p["W_aggr"].t().contiguous()      # (Fin, H)
         self.W_out, self.b_out = p["W_out"], p["b_out"]
 
 
@@ -606,8 +631,8 @@ def _seq2_forward(dims, W: Seq2Weights, xg, h0, mask, training):
     TN, H, M, K, U, Vp = T * N, dims.H, dims.M, dims.K, dims.U, dims.Vp
     f32 = dict(dtype=th.float32, device=xg.device)
     xg2 = xg.reshape(TN, dims.Fin)
-    x = th.relu_(th.addmm(W.b_aggr, xg2, W.W_aggr.t())) if dims.aggr else xg2
-    pvg = th.addmm(W.bx, x, W.Wx.t())                              # (TN, Vp + 3H) = [pv | pg], one GEMM
+    x = dense(xg2, W.W_aggr, W.b_aggr, relu=True) if dims.aggr else xg2
+    pvg = dense(x, W.Wx, W.bx)                                     # (TN, Vp + 3H) = [pv | pg], one projection
     ld = pvg.shape[1]
     h_out = th.empty(T, N, H, **f32)
     sv_gate = th.empty(T, N, 4 * H, **f32) if training else None
@@ -681,7 +706,7 @@ class AgentSequence2(th.autograd.Function):
         Gx = Sx.t() @ x                                             # (3H + Vp, H): [dW_ih[:, :H]; dW_vsq[:, :H]]
         Gh = Sh.t() @ hprev                                         # (Vp + 3H, H): [dW_vsq[:, H:]; dW_hh]
         g["W_hh"] = Gh[Vp:]
-        dx = Sx @ W.Wdx                                             # (TN, H)
+        dx = dense(Sx, W.Wdx_t)                                     # (TN, H) = [dgi | dvsq] @ [W_ih[:, :H]; W_vsq[:, :H]]
         if dims.tarmac:
             g["W_ih"] = th.cat((Gx[:H3], S[:, :H3].t() @ sv_c.view(TN, M)), 1)
             gw = th.cat((Gx[H3:], Gh[:Vp]), 1)                      # (Vp, 2H)
@@ -695,7 +720,7 @@ class AgentSequence2(th.autograd.Function):
             dpre = dx.mul_(x > 0)
             xg2 = xg.view(TN, dims.Fin)
             g["W_aggr"], g["b_aggr"] = dpre.t() @ xg2, dpre.sum(0)
-            d_xg = (dpre @ W.W_aggr).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
+            d_xg = dense(dpre, W.W_aggr_t).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         else:
             d_xg = dx.view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         grads = tuple(g.get(k) if has else None for k, has in zip(PARAM_ORDER, ctx.has))

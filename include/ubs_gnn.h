@@ -182,6 +182,10 @@ UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int Fin, int fl
                       const float* eg_u, const int64_t* eg_a, const float* eg_eps,
                       float* sv_xc, float* sv_vsq, float* sv_alpha, float* sv_gate,
                       int64_t n_rows, int n_steps, void* stream);
+/* 1 if an inference call (no save buffers) of these dimensions runs the kernel that stages each layer's weights into
+ * shared memory with bulk async copies (TMA) one layer ahead of the GEMM that consumes them, 0 if it streams weights
+ * through registers (the configuration does not fit 227 KB, or UBS_ACT_TMA=0). */
+UBS_API int ubs_agent_act_uses_tma(int H, int M, int K, int A, int U, int Fin, int flags);
 /* Reverse-time walk.  dq (n_steps,n_rows,A) and dh_last (n_rows,H, nullable) come from the loss; outputs:
  * d_xin (n_steps,n_rows,Fin), d_h0 (nullable) and the stashes st_dgi/st_dgh (.., 3H), st_dvsq (.., round4(M+2K)),
  * st_dpre (.., H) from which the caller forms the parameter gradients with batched GEMMs over the whole sequence. */

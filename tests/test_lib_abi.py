@@ -39,3 +39,13 @@ def test_cpu_tensors_are_rejected_loudly():
     from uav_bs_ctrl_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.GRUGates.apply(th.zeros(2, 6), th.zeros(2, 6), th.zeros(2, 2))
+
+
+def test_act_kernel_selection_is_a_host_side_decision():
+    """exp3 dims (H=64, msg 64, key 16, 9 actions, 8 UBS, aggregator over 2H) fit the TMA-staged act kernel;
+    H=256 does not (two layers of weights exceed shared memory) and falls back to register streaming."""
+    from uav_bs_ctrl_b200 import _lib
+    L = _lib.load()
+    assert L.ubs_agent_act_uses_tma(64, 64, 16, 9, 8, 128, 3) == 1
+    assert L.ubs_agent_act_uses_tma(64, 0, 0, 9, 1, 64, 0) == 1
+    assert L.ubs_agent_act_uses_tma(256, 64, 16, 9, 8, 512, 3) == 0

@@ -44,6 +44,7 @@ _PROTOS = {
     "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _i64, _i64, _int, _ptr]),
     "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _i64, _int, _ptr]),
     "ubs_agent_pack_size": (_i64, [_int] * 7),
+    "ubs_agent_act_uses_tma": (C.c_int, [_int] * 7),
     "ubs_agent_pack": (C.c_int, [_int] * 7 + [_F] * 15 + [_ptr]),
     "ubs_agent_seq_fwd": (C.c_int, [_int] * 7 + [_F] * 11 + [_i64, _int, _ptr]),
     "ubs_agent_act_fwd": (C.c_int, [_int] * 7 + [_F] * 14 + [_i64, _int, _ptr]),

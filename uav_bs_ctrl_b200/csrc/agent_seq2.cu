@@ -112,16 +112,20 @@ __device__ __forceinline__ void gemm_s(const float* W, int ldw, const float* A, 
     __syncthreads();
 }
 
+// Row-major global tile <-> feature-major shared tile.  A warp owns whole rows (no integer division; every global
+// access is a contiguous 128-byte row segment).
 __device__ __forceinline__ void load_tile(const float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, float* s) {
-    for (int i = threadIdx.x; i < R * F; i += NT) {
-        const int r = i / F, f = i - r * F;
-        s[f * RP + r] = r < n_valid ? __ldg(g + (row0 + r) * ld + f) : 0.f;
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < R; r += NT / 32) {
+        const float* gr = g + (row0 + r) * ld;
+        for (int f = lane; f < F; f += 32) s[f * RP + r] = r < n_valid ? __ldg(gr + f) : 0.f;
     }
 }
 __device__ __forceinline__ void store_tile(float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, const float* s) {
-    for (int i = threadIdx.x; i < R * F; i += NT) {
-        const int r = i / F, f = i - r * F;
-        if (r < n_valid) g[(row0 + r) * ld + f] = s[f * RP + r];
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < n_valid; r += NT / 32) {
+        float* gr = g + (row0 + r) * ld;
+        for (int f = lane; f < F; f += 32) gr[f] = s[f * RP + r];
     }
 }
 __device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n) {
@@ -231,8 +235,8 @@ __global__ void __launch_bounds__(NT) seq2_fwd_kernel(const Args a) {
         // gates, row-major thread mapping so that the global stores are coalesced
         float* hout = a.h_out + (size_t)t * n * H;
         float* gt = training ? a.sv_gate + (size_t)t * n * 4 * H : nullptr;
-        for (int i = threadIdx.x; i < R * H; i += NT) {
-            const int r = i / H, ch = i - r * H;
+        for (int r = threadIdx.x >> 5; r < R; r += NT / 32)
+        for (int ch = threadIdx.x & 31; ch < H; ch += 32) {
             const float rr = sigmoidf_(sGI[ch * RP + r] + sGH[ch * RP + r]);
             const float zz = sigmoidf_(sGI[(H + ch) * RP + r] + sGH[(H + ch) * RP + r]);
             const float ghn = sGH[(2 * H + ch) * RP + r];
@@ -292,8 +296,8 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
         const float* dhq = a.dhq + (size_t)t * n * H;
         float* gdgi = a.st_dgi + (size_t)t * n * a.ld_st;
         float* gdgh = a.st_dgh + (size_t)t * n * a.ld_st;
-        for (int i = threadIdx.x; i < R * H; i += NT) {
-            const int r = i / H, ch = i - r * H;
+        for (int r = threadIdx.x >> 5; r < R; r += NT / 32)
+        for (int ch = threadIdx.x & 31; ch < H; ch += 32) {
             float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f, dir = 0.f;
             if (r < n_valid) {
                 const float* g = gt + (row0 + r) * 4 * H;

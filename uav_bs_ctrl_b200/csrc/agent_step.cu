@@ -15,52 +15,11 @@
 // 16-byte shared load per 16 FMAs; small layers are split over K to keep all 256 threads busy.
 // FP32 FMA on purpose: 1e-5 parity rules out single-pass TF32, and with 16 rows per SM a 3xTF32 tcgen05 tile
 // (M >= 64) would leave 3/4 of the SMs idle.
-#include "common.cuh"
-#include "../../include/ubs_gnn.h"
+#include "agent_step.cuh"
 
 namespace ubs {
 
-constexpr int R = 16;     // agent rows per CTA tile
-constexpr int RP = 20;    // padded row stride of feature-major smem tiles (16-byte aligned)
 constexpr int NT = 256;   // threads per CTA
-
-struct StepDims {
-    int H, M, K, A, U, Fin, flags;
-    __host__ __device__ int V() const { return M + 2 * K; }                 // [v | s | q]
-    __host__ __device__ int Vp() const { return (V() + 3) & ~3; }
-    __host__ __device__ int Ap() const { return (A + 3) & ~3; }
-    __host__ __device__ bool aggr() const { return flags & UBS_STEP_AGGR; }
-    __host__ __device__ bool tarmac() const { return flags & UBS_STEP_TARMAC; }
-    __host__ __device__ int Iih() const { return tarmac() ? H + M : H; }    // GRU input width
-    __host__ __device__ int rows_per_tile() const { return tarmac() ? (R / U) * U : R; }
-};
-
-// Packed parameter buffer (floats).  "t_*" = transposed (K-major) copies for the forward GEMMs, "o_*" = original
-// row-major (out, in) copies which are K-major for the backward products.  Every offset is a multiple of 4.
-struct PackLayout {
-    int t_aggr, b_aggr, t_vsq, b_vsq, t_ih, b_ih, t_hh, b_hh, t_out, b_out;
-    int o_aggr, o_vsq, o_ih, o_hh, o_out;
-    int total;
-};
-
-__host__ __device__ inline PackLayout make_layout(const StepDims& d) {
-    PackLayout L;
-    int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    const int H = d.H, H3 = 3 * d.H;
-    L.t_aggr = take(d.aggr() ? d.Fin * H : 0);       L.b_aggr = take(d.aggr() ? H : 0);
-    L.t_vsq = take(d.tarmac() ? 2 * H * d.Vp() : 0);  L.b_vsq = take(d.tarmac() ? d.Vp() : 0);
-    L.t_ih = take(d.Iih() * H3);                      L.b_ih = take(H3);
-    L.t_hh = take(H * H3);                            L.b_hh = take(H3);
-    L.t_out = take(H * d.Ap());                       L.b_out = take(d.Ap());
-    L.o_aggr = take(d.aggr() ? H * d.Fin : 0);
-    L.o_vsq = take(d.tarmac() ? d.Vp() * 2 * H : 0);
-    L.o_ih = take(H3 * d.Iih());
-    L.o_hh = take(H3 * H);
-    L.o_out = take(d.Ap() * H);
-    L.total = o;
-    return L;
-}
 
 struct PackArgs {
     StepDims d;
@@ -206,46 +165,22 @@ __device__ __noinline__ void tile_gemm(const float* __restrict__ W, int ldw, con
 }
 
 // global (rows x F, row-major, leading dim ld) -> smem feature-major tile; rows beyond n_valid are zero.
+// Row-major global tile <-> feature-major shared tile.  A warp owns whole rows (no integer division; every global
+// access is a contiguous 128-byte row segment).
 __device__ __forceinline__ void load_tile(const float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, float* s) {
-    for (int i = threadIdx.x; i < R * F; i += NT) {
-        const int r = i / F, f = i - r * F;
-        s[f * RP + r] = r < n_valid ? __ldg(g + (row0 + r) * ld + f) : 0.f;
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < R; r += NT / 32) {
+        const float* gr = g + (row0 + r) * ld;
+        for (int f = lane; f < F; f += 32) s[f * RP + r] = r < n_valid ? __ldg(gr + f) : 0.f;
     }
 }
 __device__ __forceinline__ void store_tile(float* __restrict__ g, int64_t row0, int n_valid, int F, int64_t ld, const float* s) {
-    for (int i = threadIdx.x; i < R * F; i += NT) {
-        const int r = i / F, f = i - r * F;
-        if (r < n_valid) g[(row0 + r) * ld + f] = s[f * RP + r];
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < n_valid; r += NT / 32) {
+        float* gr = g + (row0 + r) * ld;
+        for (int f = lane; f < F; f += 32) gr[f] = s[f * RP + r];
     }
 }
-
-struct StepArgs {
-    StepDims d;
-    const float* packed;
-    // forward, sequence-strided: tensor[t] = base + t * stride (strides in floats / elements)
-    const float* xin;  int64_t st_xin;      // (T, N, Fin)
-    const float* h0;                        // (N, H) hidden state entering step 0
-    const uint32_t* mask; int64_t st_mask;  // (T, N)
-    float* h_out; int64_t st_h;             // (T, N, H)   hidden state after each step
-    float* q; int64_t st_q;                 // (T, N, A)
-    int64_t* actions; int64_t st_act;       // (T, N) argmax, nullable
-    const float* eg_u; const int64_t* eg_a; const float* eg_eps;   // epsilon-greedy: action = u <= *eps ? a : argmax
-    // saved for backward (nullable => inference)
-    float* sv_xc;   // (T, N, Iih)  [x | c]   (PyTorch GRU input order)
-    float* sv_vsq;  // (T, N, Vp)
-    float* sv_alpha;// (T, N, U)
-    float* sv_gate; // (T, N, 4H)   r | z | n | (W_hn h + b_hn)
-    int64_t N; int T;
-    // backward
-    const float* dq;       // (T, N, A)
-    const float* dh_last;  // (N, H) gradient flowing into the last hidden state, nullable
-    float* d_xin;          // (T, N, Fin)
-    float* d_h0;           // (N, H), nullable
-    float* st_dgi;         // (T, N, 3H)  stash for the batched weight-gradient GEMMs
-    float* st_dgh;         // (T, N, 3H)
-    float* st_dvsq;        // (T, N, Vp)
-    float* st_dpre;        // (T, N, H)   grad of the aggregator pre-activation
-};
 
 struct SmemPlan {
     int xin, c, x, hp, vsq, gi, gh, hn, q, alpha, scratch, total;     // offsets in floats
@@ -431,8 +366,8 @@ __global__ void __launch_bounds__(NT, 1) agent_step_bwd_kernel(const StepArgs a)
         // GRU gates backward (saved r, z, n, ghn; h_{t-1} from h_out[t-1] or h0)
         const float* gt = a.sv_gate + (size_t)t * n * 4 * H;
         const float* hprev = t > 0 ? a.h_out + (t - 1) * a.st_h : a.h0;
-        for (int i = threadIdx.x; i < R * H; i += NT) {
-            const int r = i / H, ch = i - r * H;
+        for (int r = threadIdx.x >> 5; r < R; r += NT / 32)
+        for (int ch = threadIdx.x & 31; ch < H; ch += 32) {
             float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f, dir = 0.f;
             if (r < n_valid) {
                 const float* g = gt + (row0 + r) * 4 * H;
@@ -499,8 +434,8 @@ __global__ void __launch_bounds__(NT, 1) agent_step_bwd_kernel(const StepArgs a)
         }
         if (d.aggr()) {
             const float* xc = a.sv_xc + (size_t)t * n * I;
-            for (int i = threadIdx.x; i < R * H; i += NT) {
-                const int r = i / H, ch = i - r * H;
+            for (int r = threadIdx.x >> 5; r < R; r += NT / 32)
+            for (int ch = threadIdx.x & 31; ch < H; ch += 32) {
                 const bool on = r < n_valid && __ldg(xc + (row0 + r) * I + ch) > 0.f;
                 sDPRE[ch * RP + r] = on ? sDXC[ch * RP + r] : 0.f;
             }
@@ -564,6 +499,10 @@ extern "C" UBS_API int ubs_agent_pack(int H, int M, int K, int A, int U, int Fin
     return ubs::check_launch("ubs_agent_pack");
 }
 
+extern "C" UBS_API int ubs_agent_act_uses_tma(int H, int M, int K, int A, int U, int Fin, int flags) {
+    return ubs::agent_act_fits(ubs::mk_dims(H, M, K, A, U, Fin, flags)) ? 1 : 0;
+}
+
 extern "C" UBS_API int ubs_agent_seq_fwd(int H, int M, int K, int A, int U, int Fin, int flags, const float* packed,
                                          const float* xin, const float* h0, const uint32_t* mask,
                                          float* h_out, float* q, int64_t* actions,
@@ -593,6 +532,13 @@ extern "C" UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int 
     a.eg_u = eg_u; a.eg_a = eg_a; a.eg_eps = eg_eps;
     UBS_REQUIRE(eg_u == nullptr || (eg_a && eg_eps && actions), "ubs_agent_act_fwd: incomplete epsilon-greedy arguments");
     a.sv_xc = sv_xc; a.sv_vsq = sv_vsq; a.sv_alpha = sv_alpha; a.sv_gate = sv_gate; a.N = n_rows; a.T = n_steps;
+    // inference: weights staged through shared memory by the copy engine when two layers + activations fit
+    // (UBS_ACT_TMA=0 forces the register-streaming kernel, for A/B measurements)
+    if (!training) {
+        bool handled = false;
+        const int rc = ubs::launch_agent_act(a, (cudaStream_t)stream, &handled);
+        if (handled) return rc;
+    }
     const int rpt = a.d.rows_per_tile();
     const unsigned grid = (unsigned)((n_rows + rpt - 1) / rpt);
     const size_t smem = (size_t)ubs::make_smem(a.d, false).total * sizeof(float);

@@ -179,6 +179,9 @@ def algorithmic_cost(name, meta):
         fwd, bwd = algorithmic_bytes_gat(meta)
         fl = e * (2 * fs * Hh + 6 * Hh + 8 * heads) + n * (4 * fd * Hh + 2 * Hh)
         return (fwd, fl) if name.endswith("fwd") else (bwd, 2 * fl)
+    if name.startswith("tf32x3"):                       # C (M,N) = A (M,K) B (K,N): fp32 in / out, 3 TF32 MMAs per product
+        M_, N_, K_ = meta
+        return 4 * (M_ * K_ + K_ * N_ + M_ * N_), 2 * M_ * N_ * K_
     T_, N_, ints, train = meta
     Hh, M_, K_, A_, U_, Fin, flags = ints
     tm = bool(flags & 2)
@@ -315,6 +318,13 @@ def run_ours(a):
             b_[0] += 1
             b_[1] += ms_
         (dom, meta), (cnt, tot_ms) = max(groups.items(), key=lambda kv: kv[1][1])
+
+        def group_rate(k, v):
+            b_, f_ = algorithmic_cost(k[0], k[1])
+            s_ = v[1] * 1e-3 / v[0]
+            return {"launches": v[0], "avg_us": round(1e6 * s_, 2), "GBps": round(b_ / s_ / 1e9, 1),
+                    "fp32_tflops": round(f_ / s_ / 1e12, 2)}
+
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -325,7 +335,7 @@ def run_ours(a):
         nbytes, nflops = algorithmic_cost(dom, meta)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{dom}{list(meta[:2])}")
         except (OSError, ValueError):
             pass
         avg_s = tot_ms * 1e-3 / cnt
@@ -343,7 +353,10 @@ def run_ours(a):
                               "kernel so the device runs them back to back) after the timed region",
                     "kernel_ms_per_step": {k: round(v[1], 4) for k, v in by_name.items()},
                     "kernel_calls_per_step": {k: v[0] for k, v in by_name.items()},
-                    "groups_ms": {f"{k[0]}{list(k[1][:2])}": round(v[1], 4) for k, v in groups.items()}}
+                    "groups_ms": {f"{k[0]}{list(k[1][:2])}": round(v[1], 4) for k, v in groups.items()},
+                    # per (kernel, shape) group: launches, achieved algorithmic GB/s and FP32 TFLOP/s of one launch
+                    "groups": {f"{k[0]}{list(k[1][:2])}": group_rate(k, v) for k, v in groups.items()
+                               }}
 
     # ---- CPU baseline (oracle, rank 0, N=1 only)
     cpu = None

@@ -18,6 +18,7 @@
 //    kernel in a fixed order (deterministic; no atomics on the parameter gradients).
 #include "common.cuh"
 #include "../../include/ubs_gnn.h"
+#include <stdlib.h>
 
 namespace ubs {
 
@@ -51,7 +52,10 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, size_t row
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int FS, int HEADS, int GS>
+// EPL = edges per lane per pass: the weight / destination operands of a channel (one LDS.128 + one LDS.64) are reused
+// for EPL edges, which moves the loop from shared-memory-issue bound (2 LDS : 5 FFMA) towards FFMA bound.  A lane
+// still visits its edges in the same order (beg+li, +GS, +2GS, ...), so the result is bit-identical for every EPL.
+template <int FS, int HEADS, int GS, int EPL>
 __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
     constexpr int GPW = 32 / GS;           // destination groups per warp
     constexpr int GPB = 256 / GS;          // groups per block
@@ -144,39 +148,61 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
 #pragma unroll
             for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
         }
-        for (int e = beg + li; e < end; e += GS) {
-            const size_t u = sidx ? (size_t)__ldg(sidx + e) : (size_t)e;
-            float x[FS];
-            load_row<FS>(xsrc, u, x);
+        for (int e = beg + li; e < end; e += GS * EPL) {
+            float x[EPL][FS];
+            bool ok[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int ej = e + j * GS;
+                ok[j] = ej < end;
+                if (ok[j]) {
+                    const size_t u = sidx ? (size_t)__ldg(sidx + ej) : (size_t)ej;
+                    load_row<FS>(xsrc, u, x[j]);
+                } else {
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) x[j][f] = 0.f;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < HEADS; ++k) {
                 const float4* wk = wA + k * D;
                 const float2* ck = cbuf + k * D;
                 // linear part of the score: (1+s)/2 * attn_k . (W_src x + W_dst x_v + b)
                 const float4 pk = *reinterpret_cast<const float4*>(hP + k * 8);
-                float s = lin[k];
-                s = fmaf(pk.x, x[0], s);
-                if constexpr (FS > 1) s = fmaf(pk.y, x[1], s);
-                if constexpr (FS > 2) s = fmaf(pk.z, x[2], s);
-                if constexpr (FS > 3) s = fmaf(pk.w, x[3], s);
+                float s[EPL];
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    s[j] = fmaf(pk.x, x[j][0], lin[k]);
+                    if constexpr (FS > 1) s[j] = fmaf(pk.y, x[j][1], s[j]);
+                    if constexpr (FS > 2) s[j] = fmaf(pk.z, x[j][2], s[j]);
+                    if constexpr (FS > 3) s[j] = fmaf(pk.w, x[j][3], s[j]);
+                }
 #pragma unroll 8
                 for (int d = 0; d < D; ++d) {
                     const float4 w = wk[d];
                     const float2 c = ck[d];
-                    float z = c.x;
-                    z = fmaf(w.x, x[0], z);
-                    if constexpr (FS > 1) z = fmaf(w.y, x[1], z);
-                    if constexpr (FS > 2) z = fmaf(w.z, x[2], z);
-                    if constexpr (FS > 3) z = fmaf(w.w, x[3], z);
-                    s = fmaf(c.y, fabsf(z), s);                 // (1-s)/2 * attn * |z|
-                }
-                const float mn = fmaxf(m[k], s);
-                const float sc = __expf(m[k] - mn);
-                const float p = __expf(s - mn);
-                l[k] = fmaf(l[k], sc, p);
 #pragma unroll
-                for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[f]);
-                m[k] = mn;
+                    for (int j = 0; j < EPL; ++j) {
+                        float z = c.x;
+                        z = fmaf(w.x, x[j][0], z);
+                        if constexpr (FS > 1) z = fmaf(w.y, x[j][1], z);
+                        if constexpr (FS > 2) z = fmaf(w.z, x[j][2], z);
+                        if constexpr (FS > 3) z = fmaf(w.w, x[j][3], z);
+                        s[j] = fmaf(c.y, fabsf(z), s[j]);          // (1-s)/2 * attn * |z|
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    if (ok[j]) {
+                        const float mn = fmaxf(m[k], s[j]);
+                        const float sc = __expf(m[k] - mn);
+                        const float p = __expf(s[j] - mn);
+                        l[k] = fmaf(l[k], sc, p);
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[j][f]);
+                        m[k] = mn;
+                    }
+                }
             }
         }
         // merge the per-lane online-softmax states of the group
@@ -450,14 +476,26 @@ static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
     const int64_t nd = a.n_dst > 0 ? a.n_dst : 1;
     int gs = n_edges <= 12 * nd ? 8 : (n_edges <= 96 * nd ? 16 : 32);
     while (gs < 32 && nd * gs / 32 < (int64_t)kNumSMs * 8) gs *= 2;   // small launches (act step): parallelism first
+    // two edges per lane per pass once a lane has at least two passes of work (halves the shared-memory operand
+    // traffic per edge); a launch that cannot fill the SMs keeps the lanes instead
+    int epl = (gs < 32 || n_edges >= 64 * nd) && n_edges >= 2 * gs * nd ? 2 : 1;
+    if (epl == 2 && gs > 8 && nd * (gs / 2) / 32 >= (int64_t)kNumSMs * 8 && n_edges <= 96 * nd) gs /= 2;
+    if (const char* ev = getenv("UBS_GAT_GS")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) gs = v; }
+    if (const char* ev = getenv("UBS_GAT_EPL")) { const int v = atoi(ev); if (v == 1 || v == 2) epl = v; }
     const int gpb = 256 / gs;
     int64_t need = ((int64_t)a.n_dst + gpb - 1) / gpb;
-    int64_t cap = (int64_t)kNumSMs * 4;                            // persistent: 4 resident CTAs per SM (64 regs)
+    int64_t cap = (int64_t)kNumSMs * 4;                            // persistent: up to 4 resident CTAs per SM
     const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
     const size_t smem = (size_t)H * 3 * sizeof(float4) + (size_t)gpb * (2 * H + 2) * sizeof(float) + HEADS * 8 * sizeof(float);
-    if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8><<<grid, 256, smem, st>>>(a);
-    else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16><<<grid, 256, smem, st>>>(a);
-    else gatv2_fwd_kernel<FS, HEADS, 32><<<grid, 256, smem, st>>>(a);
+    if (epl == 2) {
+        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 2><<<grid, 256, smem, st>>>(a);
+        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 2><<<grid, 256, smem, st>>>(a);
+        else gatv2_fwd_kernel<FS, HEADS, 32, 2><<<grid, 256, smem, st>>>(a);
+    } else {
+        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 1><<<grid, 256, smem, st>>>(a);
+        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 1><<<grid, 256, smem, st>>>(a);
+        else gatv2_fwd_kernel<FS, HEADS, 32, 1><<<grid, 256, smem, st>>>(a);
+    }
     return check_launch("ubs_gatv2_fwd");
 }
 

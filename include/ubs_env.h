@@ -1,0 +1,88 @@
+/* ubs_env.h — C ABI of the device-resident, vectorised MultiUbsCoverageEnv + on-device observation-graph builder.
+ *
+ * SURVEY.md §8(f) rows 1 and 2.  One call advances B independent env instances by one step and writes the NEXT
+ * observation of all of them straight into an observation packet of a sequence arena (uav_bs_ctrl_b200/arena.py),
+ * i.e. it replaces, for B envs at once and without leaving the device,
+ *   - MultiUbsCoverageEnv.step / reset / _transmit_data / get_obs / _get_reward / _get_terminate
+ *                                          (envs/mubs_cov/mubs_cov.py:85-127,129-211,213-242,296-316)
+ *   - AirToGroundChannel.estimate_chan_gain, compute_jain_fairness_index   (envs/common.py:19-25,45-55)
+ *   - GraphObservation.build_obs_graph / local_observation, MultiUbsCoverageWrapper.build_comm_graph + dgl.merge
+ *                                          (algos/madrqn/utils/env_wrappers.py:65-89,122-154)
+ *   - common.cat -> dgl.batch over the B env instances                       (algos/common.py:40-47)
+ * Arithmetic follows the reference statement by statement, including which intermediates numpy keeps in float32 and
+ * which in float64 (NEP 50 promotion, numpy >= 2; see tests/golden/make_env_golden.py) and numpy's pairwise
+ * summation order; argsort ties are broken by index (a valid np.argsort; numpy's own tie order is unspecified).
+ * Initial layouts (maps.py set_positions: host RNG) are sampled by the caller and passed to ubs_env_reset.
+ *
+ * Conventions: as ubs_gnn.h — device pointers owned by the caller, asynchronous launches on `stream`, 0 = success,
+ * message through ubs_last_error().  The config struct is passed by host pointer and copied into the launch.
+ */
+#ifndef UBS_ENV_H_
+#define UBS_ENV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define UBS_ENV_API __attribute__((visibility("default")))
+#else
+#define UBS_ENV_API
+#endif
+
+#define UBS_ENV_MAX_ACTIONS 33
+#define UBS_ENV_MAX_UBS 32
+#define UBS_ENV_INFO 8 /* doubles per env: ep_ret, total_throughput, n_colls, avg_global_util, fair_idx, global_util, t, - */
+
+/* Static parameters of a map + env (maps.py:7-34, mubs_cov.py:13-66); every derived constant is computed by the host
+ * with the reference's own expression so that it is bit-identical (uav_bs_ctrl_b200/envs.py). */
+typedef struct {
+    int32_t n_ubs, n_gts, n_rbs, n_actions, episode_limit, fair_service, avoid_collision, reserved;
+    double range_pos, r_cov, r_sns, r_comm; /* metres; r_sns / r_comm may be +inf */
+    double dt, rew_scale;                   /* maps.py: dt, reward_scale_rate */
+    double h_ubs, p_tx, n0, bw;             /* mubs_cov.py:14-17 */
+    double c_fspl;                          /* 4 * pi * fc                    (common.py:52) */
+    double chan_a, chan_b, k_los, k_nlos;   /* a, b, 10**(eta_los/20), 10**(eta_nlos/20) (common.py:31-54) */
+    double max_rate;                        /* mubs_cov.py:36-39 */
+    double safe_dist, penalty;              /* mubs_cov.py:20-21 */
+    double moves[UBS_ENV_MAX_ACTIONS][2];   /* avail_moves (mubs_cov.py:61-65) */
+} ubs_env_cfg;
+
+/* Per-env state, all device pointers, B envs back to back. */
+typedef struct {
+    double* pos_ubs;   /* (B, U, 2)  float64 like the reference (maps.py returns float64 UBS positions) */
+    float* pos_gts;    /* (B, G, 2)  float32 (maps.py:107) */
+    float* avg_rate;   /* (B, G)     avg_rate_per_gt */
+    float* rate;       /* (B, G)     rate_per_gt of the last step */
+    int32_t* prior;    /* (B, G)     prior_gts: GT ids, highest priority first */
+    int32_t* t;        /* (B)        timer */
+    double* info;      /* (B, UBS_ENV_INFO) */
+    int32_t* sched;    /* (B, G, 2)  (serving UBS, RB) of each GT or (-1,-1); diagnostic / tests */
+} ubs_env_state;
+
+/* Where one observation packet lives (word = 4 bytes; offsets from `packet`; uav_bs_ctrl_b200/arena.py PacketLayout). */
+typedef struct {
+    int32_t* packet;
+    int64_t off_x_gt, off_x_ubs, off_x_agent, off_ip_seen, off_ip_near, off_mask, off_rew, off_done, off_bad;
+} ubs_env_packet;
+
+/* Words of device scratch ubs_env_step / ubs_env_reset need for B envs (staging of the per-env compacted rows). */
+UBS_ENV_API int64_t ubs_env_scratch_words(const ubs_env_cfg* cfg, int64_t B);
+
+/* reset(): t = 0, running averages cleared, positions / initial priorities as currently stored in `st`
+ * (the caller has just written pos_ubs, pos_gts, prior), one _transmit_data, observation -> packet with
+ * reward = 0, done = bad = 0.                                                                                       */
+UBS_ENV_API int ubs_env_reset(const ubs_env_cfg* cfg, const ubs_env_state* st, const ubs_env_packet* pk, int32_t* scratch,
+                              int64_t B, void* stream);
+
+/* step(actions): actions (B*U) int64 (what the fused act kernel writes).  Writes the next observation, the reward of
+ * this transition, done and bad_mask (t == episode_limit) into the packet.                                          */
+UBS_ENV_API int ubs_env_step(const ubs_env_cfg* cfg, const ubs_env_state* st, const int64_t* actions,
+                             const ubs_env_packet* pk, int32_t* scratch, int64_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBS_ENV_H_ */

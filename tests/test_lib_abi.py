@@ -1,4 +1,4 @@
-"""CPU: the C-ABI library loads and exports every symbol include/ubs_gnn.h declares (no compute calls)."""
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares (no compute calls)."""
 import ctypes
 import os
 import re
@@ -9,14 +9,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_symbols():
-    src = open(os.path.join(ROOT, "include", "ubs_gnn.h")).read()
-    return sorted(set(re.findall(r"UBS_API\s+[\w\s\*]+?\b(ubs_\w+)\s*\(", src)))
+    syms = set()
+    for h in ("ubs_gnn.h", "ubs_env.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        syms |= set(re.findall(r"UBS(?:_ENV)?_API\s+[\w\s\*]+?\b(ubs_\w+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_header_declares_expected_entry_points():
     syms = _header_symbols()
     for s in ("ubs_version", "ubs_last_error", "ubs_gatv2_fwd", "ubs_gatv2_bwd", "ubs_block_attn_fwd",
-              "ubs_block_attn_bwd", "ubs_gru_gates_fwd", "ubs_gru_gates_bwd"):
+              "ubs_block_attn_bwd", "ubs_gru_gates_fwd", "ubs_gru_gates_bwd", "ubs_env_reset", "ubs_env_step",
+              "ubs_env_scratch_words"):
         assert s in syms
 
 
@@ -26,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         _lib.build()
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for s in _header_symbols():
-        assert hasattr(lib, s), f"{s} declared in ubs_gnn.h but not exported"
+        assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
     assert set(_lib.exported_symbols()) == set(_header_symbols())
     loaded = _lib.load()
     assert loaded.ubs_version() == 100

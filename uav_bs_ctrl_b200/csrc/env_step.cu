@@ -1,0 +1,154 @@
+// Device-resident vectorised MultiUbsCoverageEnv + on-device observation-graph builder (include/ubs_env.h).
+//
+// Kernel 1 (env_step_kernel): one CTA per env instance runs env_core.h's env_run — move, distances, channel gains,
+// greedy RB scheduling, rates, running averages, fairness, reward, visibility — with the env's working set in shared
+// memory, and leaves the env's visible GT / UBS rows compacted in (agent, slot) order in a staging area.
+// Kernel 2 (env_pack_kernel): one CTA per env turns the per-agent degrees of ALL envs into the packet's global
+// `indptr` (exclusive prefix over the B*U agent rows) and copies the staged rows to their place in `x_gt` / `x_ubs`:
+// the node / edge order of the reference's dgl.batch(per-agent graphs) + dgl.merge + dgl.batch(envs)
+// (env_wrappers.py:65-89,137; algos/common.py:40-47) by pointer arithmetic, no graph objects.
+//
+// Compiled with -fmad=false (see Makefile): the env arithmetic must round like numpy's separate multiply / add.
+#include "common.cuh"
+#include "env_core.h"
+
+namespace ubs_env {
+
+struct DevCtx {
+    int tid, nthr;
+    __device__ void sync() const { __syncthreads(); }
+};
+
+struct StepArgs {
+    ubs_env_cfg cfg;
+    ubs_env_state st;
+    ubs_env_packet pk;
+    const int64_t* actions;
+    int32_t* scratch;
+    int64_t B;
+    int is_reset;
+};
+
+__global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ double smem_d[];
+    const ubs_env_cfg& c = a.cfg;
+    Work w;
+    w.carve(smem_d, c.n_ubs, c.n_gts, c.n_rbs);
+    const Scratch sc(c, a.B);
+    const int64_t b = blockIdx.x;
+    EnvOut o;
+    o.x_agent = reinterpret_cast<float*>(a.pk.packet + a.pk.off_x_agent);
+    o.mask = a.pk.packet + a.pk.off_mask;
+    o.rew = reinterpret_cast<float*>(a.pk.packet + a.pk.off_rew);
+    o.done = reinterpret_cast<float*>(a.pk.packet + a.pk.off_done);
+    o.bad = reinterpret_cast<float*>(a.pk.packet + a.pk.off_bad);
+    o.stage_gt = reinterpret_cast<float*>(a.scratch + sc.off_stage_gt + b * sc.gt_stride);
+    o.stage_ubs = reinterpret_cast<float*>(a.scratch + sc.off_stage_ubs + b * sc.ubs_stride);
+    o.deg_seen = a.scratch + sc.off_deg_seen;
+    o.deg_near = a.scratch + sc.off_deg_near;
+    DevCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    env_run(c, a.st, b, a.actions, a.is_reset != 0, w, o, ctx);
+}
+
+__device__ __forceinline__ int block_sum_128(int v, int* red) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const int tot = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(128) env_pack_kernel(const __grid_constant__ StepArgs a) {
+    __shared__ int red[4];
+    __shared__ int offs[2][UBS_ENV_MAX_UBS + 1];
+    const ubs_env_cfg& c = a.cfg;
+    const Scratch sc(c, a.B);
+    const int U = c.n_ubs, Fg = c.fair_service ? 4 : 3;
+    const int64_t b = blockIdx.x, N = a.B * U;
+    const int32_t* deg_seen = a.scratch + sc.off_deg_seen;
+    const int32_t* deg_near = a.scratch + sc.off_deg_near;
+    int s1 = 0, s2 = 0;
+    for (int64_t i = threadIdx.x; i < b * U; i += 128) { s1 += deg_seen[i]; s2 += deg_near[i]; }
+    const int base_seen = block_sum_128(s1, red);
+    const int base_near = block_sum_128(s2, red);
+    if (threadIdx.x == 0) {
+        int p1 = 0, p2 = 0;
+        for (int i = 0; i < U; ++i) {
+            offs[0][i] = p1; offs[1][i] = p2;
+            p1 += deg_seen[b * U + i]; p2 += deg_near[b * U + i];
+        }
+        offs[0][U] = p1; offs[1][U] = p2;
+    }
+    __syncthreads();
+    int32_t* ip_seen = a.pk.packet + a.pk.off_ip_seen;
+    int32_t* ip_near = a.pk.packet + a.pk.off_ip_near;
+    if (threadIdx.x < U) {
+        ip_seen[b * U + threadIdx.x] = base_seen + offs[0][threadIdx.x];
+        ip_near[b * U + threadIdx.x] = base_near + offs[1][threadIdx.x];
+    }
+    if (b == a.B - 1 && threadIdx.x == 0) {
+        ip_seen[N] = base_seen + offs[0][U];
+        ip_near[N] = base_near + offs[1][U];
+    }
+    const int32_t* sg = a.scratch + sc.off_stage_gt + b * sc.gt_stride;
+    int32_t* xg = a.pk.packet + a.pk.off_x_gt + (int64_t)base_seen * Fg;
+    for (int i = threadIdx.x; i < offs[0][U] * Fg; i += 128) xg[i] = sg[i];
+    const int32_t* su = a.scratch + sc.off_stage_ubs + b * sc.ubs_stride;
+    int32_t* xu = a.pk.packet + a.pk.off_x_ubs + (int64_t)base_near * 2;
+    for (int i = threadIdx.x; i < offs[1][U] * 2; i += 128) xu[i] = su[i];
+}
+
+static int check_cfg(const ubs_env_cfg* c, const char* fn) {
+    using ubs::set_error;
+    if (!c) { set_error("%s: NULL config", fn); return 2; }
+    if (c->n_ubs < 1 || c->n_ubs > UBS_ENV_MAX_UBS) { set_error("%s: n_ubs must be in [1, %d] (got %d)", fn, UBS_ENV_MAX_UBS, c->n_ubs); return 2; }
+    if (c->n_gts < 1 || c->n_gts > 4096) { set_error("%s: n_gts must be in [1, 4096] (got %d)", fn, c->n_gts); return 2; }
+    if (c->n_rbs < 1 || c->n_rbs > 64) { set_error("%s: n_rbs must be in [1, 64] (got %d)", fn, c->n_rbs); return 2; }
+    if (c->n_actions < 1 || c->n_actions > UBS_ENV_MAX_ACTIONS) { set_error("%s: n_actions must be in [1, %d] (got %d)", fn, UBS_ENV_MAX_ACTIONS, c->n_actions); return 2; }
+    if (!(c->range_pos > 0) || !(c->max_rate > 0)) { set_error("%s: range_pos / max_rate must be positive", fn); return 2; }
+    return 0;
+}
+
+static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* st, const int64_t* actions,
+                  const ubs_env_packet* pk, int32_t* scratch, int64_t B, bool is_reset, void* stream) {
+    if (int rc = check_cfg(cfg, fn)) return rc;
+    UBS_REQUIRE(st && pk && scratch, "%s: NULL argument", fn);
+    UBS_REQUIRE(st->pos_ubs && st->pos_gts && st->avg_rate && st->rate && st->prior && st->t && st->info && st->sched,
+                "%s: NULL state pointer", fn);
+    UBS_REQUIRE(pk->packet != nullptr, "%s: NULL packet", fn);
+    UBS_REQUIRE(is_reset || actions != nullptr, "%s: NULL actions", fn);
+    UBS_REQUIRE(B >= 0 && B * cfg->n_ubs < (1ll << 31) / (cfg->n_gts > 0 ? cfg->n_gts : 1), "%s: batch out of range", fn);
+    if (B == 0) return 0;
+    StepArgs a;
+    a.cfg = *cfg; a.st = *st; a.pk = *pk; a.actions = actions; a.scratch = scratch; a.B = B; a.is_reset = is_reset ? 1 : 0;
+    const size_t smem = Work::bytes(cfg->n_ubs, cfg->n_gts, cfg->n_rbs);
+    UBS_REQUIRE(smem <= 227 * 1024, "%s: env working set (%zu B) exceeds shared memory", fn, smem);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = smem;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    env_step_kernel<<<(unsigned)B, 128, smem, s>>>(a);
+    if (int rc = ubs::check_launch(fn)) return rc;
+    env_pack_kernel<<<(unsigned)B, 128, 0, s>>>(a);
+    return ubs::check_launch(fn);
+}
+
+}  // namespace ubs_env
+
+extern "C" UBS_ENV_API int64_t ubs_env_scratch_words(const ubs_env_cfg* cfg, int64_t B) {
+    if (!cfg || B < 0) return -1;
+    return ubs_env::Scratch(*cfg, B).words;
+}
+
+extern "C" UBS_ENV_API int ubs_env_reset(const ubs_env_cfg* cfg, const ubs_env_state* st, const ubs_env_packet* pk,
+                                         int32_t* scratch, int64_t B, void* stream) {
+    return ubs_env::launch("ubs_env_reset", cfg, st, nullptr, pk, scratch, B, true, stream);
+}
+
+extern "C" UBS_ENV_API int ubs_env_step(const ubs_env_cfg* cfg, const ubs_env_state* st, const int64_t* actions,
+                                        const ubs_env_packet* pk, int32_t* scratch, int64_t B, void* stream) {
+    return ubs_env::launch("ubs_env_step", cfg, st, actions, pk, scratch, B, false, stream);
+}

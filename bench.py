@@ -179,6 +179,10 @@ def algorithmic_cost(name, meta):
         fwd, bwd = algorithmic_bytes_gat(meta)
         fl = e * (2 * fs * Hh + 6 * Hh + 8 * heads) + n * (4 * fd * Hh + 2 * Hh)
         return (fwd, fl) if name.endswith("fwd") else (bwd, 2 * fl)
+    if name == "env_step":                              # state in + out, staged rows + packet rows, per env instance
+        B_, U_, G_, Fg = meta
+        words = U_ * 4 * 2 + G_ * 2 + 4 * G_ * 2 + 2 * (U_ * G_ * Fg + U_ * (U_ - 1) * 2) + 6 * U_ + 2 * G_
+        return 4 * B_ * words, B_ * U_ * G_ * 60
     if name.startswith("tf32x3"):                       # C (M,N) = A (M,K) B (K,N): fp32 in / out, 3 TF32 MMAs per product
         M_, N_, K_ = meta
         return 4 * (M_ * K_ + K_ * N_ + M_ * N_), 2 * M_ * N_ * K_
@@ -279,6 +283,42 @@ def run_ours(a):
         e2e = {"value": world * B * T * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps}
 
+    # ---- full loop: the device-resident env (ubs_env_step) closes the loop — reset, T x (act -> env.step), update, with
+    # nothing returning to the host; initial layouts come from the RNG-matched host sampler, drawn ahead of time
+    full = None
+    if use_arena and not a.no_full:
+        from uav_bs_ctrl_b200 import envs as E
+        m = E.DenseHotSpot(n_ubs=U, n_grps=G // 5, gts_per_grp=5, episode_limit=T)
+        env = E.MultiUbsCoverageVecEnv(n_envs=B, device=dev, map=m)
+        pool = env.make_layout_pool(4, seed0=10_000 * (rank + 1))
+        cyc = [0]
+
+        def full_step():
+            learner.begin_sequence(arena)
+            env.reset(arena, 0, layouts=pool[cyc[0] % len(pool)])
+            cyc[0] += 1
+            learner.rollout_arena(env, arena, eps)
+            return learner.update_arena(arena, sync=False)
+
+        ms_f, launches_f, _ = timed(full_step, a.steps, a.warmup)
+        deg = float(arena.sec("ip_seen")[:, -1].float().mean()) / (B * U)
+        ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        env.reset(arena, 0, layouts=pool[0])
+        ev0.record()
+        for t in range(T):                                # env alone: 2 kernels per step (step + pack), eager launches
+            env.step(arena, t)
+        ev1.record()
+        th.cuda.synchronize()
+        env_us = 1e3 * ev0.elapsed_time(ev1) / T
+        full = {"value": world * B * T * a.steps / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / a.steps,
+                "gpu_launches": int(launches_f), "mean_seen_degree": deg, "env_step_us": env_us,
+                "env_steps_per_sec_env_alone": B / (env_us * 1e-6),
+                "env": f"device-resident MultiUbsCoverageEnv, DenseHotSpot {U} UBS x {G} GT (maps.py:83-113), "
+                       f"episode_limit {T}, eps-greedy {eps}; resets from a pool of {len(pool)} x {B} RNG-matched layouts; "
+                       "one CUDA graph per rollout" + ("" if learner.args.cuda_graphs else " (graphs off)")}
+        for t in range(T + 1):                            # the value / roofline passes below replay the synthetic episode
+            arena.load(t, packets[t])
+
     # ---- where the step goes: act loop (T replayed graphs) vs update, 3 extra cycles (every rank: all-reduce inside)
     phases = None
     if use_arena:
@@ -375,7 +415,8 @@ def run_ours(a):
                            "parallelism": f"dp{world}", "path": a.path + ("" if a.no_graphs or a.path != "arena" else "+cudagraphs"),
                            "l2_policy": "inputs exceed L2: "
                            f"{h2d / 2**20:.0f} MiB of observations are streamed per step (> 126 MB L2)"},
-                "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "e2e": e2e, "full_loop": full,
+                "clocks": clocks,
                 "gpu_launches": int(launches)}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -461,6 +502,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="arena path without CUDA-graph replay of the act step")
     ap.add_argument("--act-seq2", action="store_true", help="act step through the resident-weight kernel (T=1) + small GEMMs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the full-loop leg (device env in the loop)")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -245,10 +245,22 @@ class EnvBuffers:
         return s
 
     def set_layout(self, pos_ubs, pos_gts, prior):
-        as_t = lambda a, dt: th.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.device, non_blocking=True)
+        def as_t(a, dt):
+            if not isinstance(a, th.Tensor):
+                a = th.as_tensor(np.ascontiguousarray(a))
+            return a.to(device=self.device, dtype=dt, non_blocking=True)
         self.pos_ubs.copy_(as_t(pos_ubs, th.float64).view_as(self.pos_ubs))
         self.pos_gts.copy_(as_t(pos_gts, th.float32).view_as(self.pos_gts))
         self.prior.copy_(as_t(prior, th.int32).view_as(self.prior))
+
+    _STATE = ("pos_ubs", "pos_gts", "avg_rate", "rate", "prior", "t", "info", "sched")
+
+    def snapshot(self):
+        return {n: getattr(self, n).clone() for n in self._STATE}
+
+    def restore(self, snap):
+        for n in self._STATE:
+            getattr(self, n).copy_(snap[n])
 
     def info_dict(self, b: int = 0) -> dict:
         v = self.info[b].tolist()
@@ -302,6 +314,15 @@ class MultiUbsCoverageVecEnv:
         from .arena import PacketLayout
         return PacketLayout(self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 2, F_gt or (4 if self.cfg.fair_service else 3), 2)
 
+    def make_layout_pool(self, n_batches: int, seed0: int = 0):
+        """``n_batches`` RNG-matched reset batches sampled ahead of time and parked on the device (the host sampler is
+        python + numpy RNG code, ~0.3 ms per instance: far slower than the device loop it feeds)."""
+        pool = []
+        for k in range(n_batches):
+            pu, pg, pr = sample_layouts(self.map, [seed0 + k * self.n_envs + b for b in range(self.n_envs)])
+            pool.append(tuple(th.as_tensor(a).to(self.device) for a in (pu, pg, pr)))
+        return pool
+
     def _check(self, arena):
         L = arena.layout
         if (L.B, L.U, L.G, L.F_gt) != (self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 4 if self.cfg.fair_service else 3):
@@ -331,6 +352,8 @@ class MultiUbsCoverageVecEnv:
         acts = arena.acts[t] if actions is None else actions
         if not acts.is_cuda or acts.dtype != th.int64 or acts.numel() != self.n_envs * self.n_agents:
             raise ValueError("actions must be a CUDA int64 tensor of B*U elements")
+        from . import ops
         pk = packet_struct(arena.layout, arena.buf[t + 1])
-        _lib.check(self._lib.ubs_env_step(C.byref(self.cfg), C.byref(self._state), acts.data_ptr(), C.byref(pk),
-                                          self.buf.scratch.data_ptr(), self.n_envs, _lib.stream()), "ubs_env_step")
+        with ops._timed("env_step", (self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 4 if self.cfg.fair_service else 3)):
+            _lib.check(self._lib.ubs_env_step(C.byref(self.cfg), C.byref(self._state), acts.data_ptr(), C.byref(pk),
+                                              self.buf.scratch.data_ptr(), self.n_envs, _lib.stream()), "ubs_env_step")

@@ -289,6 +289,49 @@ class MultiAgentQLearner:
         _lib.add_launches(g[1])
         return arena.acts[t]
 
+    def rollout_arena(self, env, arena, eps_thres):
+        """One whole episode window on the device env (``envs.MultiUbsCoverageVecEnv``): for t in 0..T-1 the fused act
+        step on slot t, then ``env.step`` writing observation / reward / done of slot t+1 — the reference's
+        ``act -> env.step -> cache`` loop (``algos/madrqn/run.py:81-90``) with nothing returning to the host.  With
+        ``args.cuda_graphs`` all 5·T kernels are captured once per (arena, env) and replayed as ONE graph launch."""
+        T = self.max_seq_len
+        if not hasattr(self, "_eps_dev"):
+            self._eps_dev = th.zeros((), device=self.device)
+            self._eps_host, self._act_graphs = None, {}
+        if self._eps_host != eps_thres:
+            self._eps_dev.fill_(float(eps_thres))
+            self._eps_host = eps_thres
+
+        def run():
+            for t in range(T):
+                self._act_arena_eager(arena, t)
+                env.step(arena, t)
+
+        from . import ops
+        if not getattr(self.args, "cuda_graphs", False) or ops.TIMER is not None:
+            run()
+            return
+        key = ("rollout", id(arena), id(env))
+        g = self._act_graphs.get(key)
+        if g is None:
+            self.policy_net._packed(self.policy_net.arena_dims(arena), self.policy_net._fused_params())
+            snap = env.buf.snapshot()                    # the warm-up step below must not advance the episode
+            side = th.cuda.Stream()
+            side.wait_stream(th.cuda.current_stream())
+            with th.cuda.stream(side):
+                self._act_arena_eager(arena, 0)          # warm-up outside capture (slot 1 is rewritten by the replay)
+                env.step(arena, 0)
+            th.cuda.current_stream().wait_stream(side)
+            env.buf.restore(snap)
+            g = th.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with th.cuda.graph(g):
+                run()
+            g = (g, _lib.launch_count() - n0)
+            self._act_graphs[key] = g
+        g[0].replay()
+        _lib.add_launches(g[1])
+
     def update_arena(self, arena, sync=True):
         """One BPTT update on the window held by ``arena`` (same math as ``update``; no graph objects, no re-batching):
         one strided-segment encoder launch per relation over all T+1 timesteps and one persistent recurrent kernel,

@@ -82,6 +82,10 @@ UBS_ENV_API int ubs_env_reset(const ubs_env_cfg* cfg, const ubs_env_state* st, c
 UBS_ENV_API int ubs_env_step(const ubs_env_cfg* cfg, const ubs_env_state* st, const int64_t* actions,
                              const ubs_env_packet* pk, int32_t* scratch, int64_t B, void* stream);
 
+/* Diagnostic: with UBS_ENV_PROFILE=1 in the environment, CTA 0 stamps clock64() after every phase barrier of the step
+ * kernel; this copies the 32 stamps of the last launch to the host (synchronises the device).                        */
+UBS_ENV_API int ubs_env_phase_clocks(int64_t* out32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,7 @@ _PROTOS = {
     "ubs_agent_seq_bwd": (C.c_int, [_int] * 7 + [_F] * 15 + [_i64, _int, _ptr]),
     # include/ubs_env.h (config / state / packet structs travel by host pointer)
     "ubs_env_scratch_words": (_i64, [_ptr, _i64]),
+    "ubs_env_phase_clocks": (C.c_int, [_ptr]),
     "ubs_env_reset": (C.c_int, [_ptr, _ptr, _ptr, _I, _i64, _ptr]),
     "ubs_env_step": (C.c_int, [_ptr, _ptr, _I, _ptr, _I, _i64, _ptr]),
 }

@@ -21,39 +21,57 @@
 namespace ubs_env {
 
 // numpy's pairwise summation of a contiguous float32 vector (numpy/_core/src/umath/loops_utils.h.src): what
-// ndarray.sum() / np.mean() of a 1-D float32 array computes.
-UBS_HD inline float np_sum_f32(const float* a, int n) {
+// ndarray.sum() / np.mean() of a 1-D float32 array computes.  `at(i)` yields element i; the recursion of the original
+// (blocks of <= 128 elements, halves rounded to multiples of 8) is unrolled at compile time (2 levels: n <= 512 = the n_gts limit of the env).
+template <class F>
+UBS_HD inline float np_sum_block(const F& at, int lo, int n) {
     if (n < 8) {
         float res = -0.0f;
-        for (int i = 0; i < n; ++i) res += a[i];
+        for (int i = 0; i < n; ++i) res += at(lo + i);
         return res;
     }
-    if (n <= 128) {
-        float r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
-        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i];
-        return res;
+    float r0 = at(lo), r1 = at(lo + 1), r2 = at(lo + 2), r3 = at(lo + 3), r4 = at(lo + 4), r5 = at(lo + 5),
+          r6 = at(lo + 6), r7 = at(lo + 7);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += at(lo + i); r1 += at(lo + i + 1); r2 += at(lo + i + 2); r3 += at(lo + i + 3);
+        r4 += at(lo + i + 4); r5 += at(lo + i + 5); r6 += at(lo + i + 6); r7 += at(lo + i + 7);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_sum_f32(a, n2) + np_sum_f32(a + n2, n - n2);
+    float res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += at(lo + i);
+    return res;
+}
+template <int DEPTH, class F>
+UBS_HD inline float np_sum_rec(const F& at, int lo, int n) {
+    if constexpr (DEPTH == 0) {
+        return np_sum_block(at, lo, n);
+    } else {
+        if (n <= 128) return np_sum_block(at, lo, n);
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_sum_rec<DEPTH - 1>(at, lo, n2) + np_sum_rec<DEPTH - 1>(at, lo + n2, n - n2);
+    }
+}
+template <class F>
+UBS_HD inline float np_sum_fn(const F& at, int n) { return np_sum_rec<2>(at, 0, n); }
+#if defined(__CUDACC__)
+__noinline__          // one copy of the unrolled blocks for the three call sites
+#endif
+UBS_HD inline float np_sum_f32(const float* a, int n) {
+    return np_sum_fn([a](int i) { return a[i]; }, n);
 }
 
 // Carves the per-env workspace (shared memory on the device) out of one 8-byte aligned buffer.
 struct Work {
     double *pos_u, *gain;
-    float *pos_g, *d_u2g, *d_u2u, *pitf, *rate, *avg, *tmp, *tmp2, *scal;
-    int *prior, *occ, *nsch, *sch_ubs, *sch_rb, *slot, *nslot, *deg;
+    float *pos_g, *d_u2g, *d_u2u, *pitf, *rate, *avg, *tmp, *tmp2, *f_rate, *f_avg, *scal;
+    int *prior, *occ, *nsch, *sch_ubs, *sch_rb, *slot, *nslot, *deg, *ncov;
     unsigned char* order;
 
     UBS_HD static size_t bytes(int U, int G, int R) {
         size_t n = 8 * ((size_t)U * 2 + (size_t)U * G);
-        n += 4 * ((size_t)G * 2 + (size_t)U * G + (size_t)U * U + (size_t)U * G + 4 * (size_t)G + 8);
-        n += 4 * ((size_t)G + (size_t)U * R + U + 2 * (size_t)G + (size_t)U * G + (size_t)U * U + 4 * (size_t)U + 4);
+        n += 4 * ((size_t)G * 2 + (size_t)U * G + (size_t)U * U + (size_t)U * G + 6 * (size_t)G + 8);
+        n += 4 * ((size_t)G + (size_t)U * R + U + 3 * (size_t)G + (size_t)U * G + (size_t)U * U + 5 * (size_t)U + 4);
         n += (size_t)G * U;
         return (n + 15) & ~(size_t)15;
     }
@@ -70,6 +88,8 @@ struct Work {
         avg = f; f += G;
         tmp = f; f += G;
         tmp2 = f; f += G;
+        f_rate = f; f += G;
+        f_avg = f; f += G;
         scal = f; f += 8;
         int* i = (int*)f;
         prior = i; i += G;
@@ -79,7 +99,8 @@ struct Work {
         sch_rb = i; i += G;
         slot = i; i += (size_t)U * G;
         nslot = i; i += U * U;
-        deg = i; i += 4 * U + 4;          // deg_seen[U] | deg_near[U] | off_seen[U] | off_near[U] | totals
+        deg = i; i += 5 * U + 4;          // deg_seen[U] | deg_near[U] | off_seen[U] | off_near[U] | not-idle[U]
+        ncov = i; i += G;
         order = (unsigned char*)i;
     }
 };
@@ -87,6 +108,7 @@ struct Work {
 struct SerialCtx {
     int tid = 0, nthr = 1;
     void sync() const {}
+    void mark(int) const {}
 };
 
 // Where the results of env b go.
@@ -98,12 +120,73 @@ struct EnvOut {
     float* bad;         // (B)
     float* stage_gt;    // this env's staging rows (U*G, F_gt): compacted in (agent, slot) order
     float* stage_ubs;   // (U*(U-1), 2)
-    int32_t* deg_seen;  // (N) all envs
-    int32_t* deg_near;  // (N)
+    int32_t* off_seen;  // (N) all envs: env-local exclusive prefix of the seen degrees
+    int32_t* off_near;  // (N)
+    int32_t* tot;       // (B, 2): seen / near rows of each env
 };
 
-// scal[] slots
-enum { S_FAIR = 0, S_GU = 1, S_MEAN = 2, S_AGU = 3, S_TPUT = 4 };
+
+// ---- device-only helpers: warp-cooperative versions of the two serial phases (same arithmetic, same order) --------
+#if defined(__CUDA_ARCH__)
+template <int UMAX>
+__device__ __forceinline__ float itf_sum(float p, unsigned occb) {
+    float v = 0.f;
+#pragma unroll
+    for (int i2 = 0; i2 < UMAX; ++i2) {
+        const float pi = __shfl_sync(0xffffffffu, p, i2);
+        v += ((occb >> i2) & 1u) ? pi : 0.f;
+    }
+    return v;
+}
+
+// Greedy RB scheduling by warp 0.  Lane rb owns resource block rb (bit i of `occb` = UBS i transmits on it); the
+// interference sum of a block is accumulated over the UBSs in index order exactly like the serial loop.
+__device__ inline void sched_warp(const ubs_env_cfg& c, const Work& w, int lane) {
+    const int U = c.n_ubs, G = c.n_gts, R = c.n_rbs;
+    int* list = w.slot;                                   // scratch (the compaction slots are computed later)
+    int cnt = 0;
+    for (int k0 = 0; k0 < G; k0 += 32) {                  // covered GTs in priority order
+        const int k = k0 + lane;
+        const int m = k < G ? w.prior[k] : -1;
+        const bool f = m >= 0 && w.ncov[m] > 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) list[cnt + __popc(bal & ((1u << lane) - 1u))] = m;
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+    unsigned occb = 0;                                    // lane rb: UBSs transmitting on RB rb
+    unsigned long long nsch = 0;                          // uniform: 4 bits per UBS (U <= 16, R <= 15)
+    int m_next = cnt > 0 ? list[0] : 0;
+    for (int q = 0; q < cnt; ++q) {
+        const int m = m_next;
+        if (q + 1 < cnt) m_next = list[q + 1];            // off the critical path
+        const float p = lane < U ? w.pitf[lane * G + m] : 0.f;
+        const int nc = w.ncov[m];
+        int i = -1;
+        for (int j = 0; j < nc; ++j) {                    // nearest covering UBS with a free RB
+            const int cand = w.order[(size_t)m * U + j];
+            if ((int)((nsch >> (4 * cand)) & 15ull) < R) { i = cand; break; }
+        }
+        if (i < 0) continue;                              // warp-uniform
+        // interference on RB `lane` if m were served there: the UBSs already on that RB, added in index order
+        // (adding +0.f for the others / for i2 >= U leaves the non-negative sum unchanged bit for bit)
+        const float v = U <= 8 ? itf_sum<8>(p, occb) : itf_sum<16>(p, occb);
+        const bool idle = lane < R && !((occb >> i) & 1u);
+        // first minimum among the idle RBs: v >= +0, so the uint order of the bit patterns is the float order
+        const unsigned key = idle ? __float_as_uint(v) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        const int best = __ffs(__ballot_sync(0xffffffffu, key == kmin)) - 1;
+        if (lane == best) occb |= 1u << i;
+        nsch += 1ull << (4 * i);
+        if (lane == 0) {
+            w.occ[i * R + best] = m;
+            w.sch_ubs[m] = i;
+            w.sch_rb[m] = best;
+        }
+    }
+    __syncwarp();
+}
+#endif
 
 template <class Ctx>
 UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_t b, const int64_t* actions,
@@ -113,8 +196,12 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
     const int Fg = c.fair_service ? 4 : 3;
     double* info = st.info + b * UBS_ENV_INFO;
 
+    // running episode statistics: fetched now by thread 0 so that their latency hides behind the whole step
+    double inf0 = 0.0, inf1 = 0.0, inf2 = 0.0, inf3 = 0.0;
+    if (tid == 0 && !is_reset) { inf0 = info[0]; inf1 = info[1]; inf2 = info[2]; inf3 = info[3]; }
+
     // ---- load state; step(): self.t += 1; pos_ubs = clip(pos_ubs + avail_moves[actions], 0, range_pos)  (:105-109)
-    int t = is_reset ? 0 : st.t[b] + 1;
+    const int t = is_reset ? 0 : st.t[b] + 1;
     for (int i = tid; i < U * 2; i += nthr) {
         double p = st.pos_ubs[b * U * 2 + i];                              // np: float64
         if (!is_reset) {
@@ -135,8 +222,9 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         w.sch_rb[m] = -1;
     }
     for (int i = tid; i < U * R; i += nthr) w.occ[i] = -1;
-    for (int i = tid; i < U; i += nthr) w.nsch[i] = 0;
+    for (int i = tid; i < U; i += nthr) { w.nsch[i] = 0; w.deg[4 * U + i] = 0; }
     ctx.sync();
+    ctx.mark(1);
 
     // ---- _transmit_data step 1: distances (:133-139).  np: norm of a float64 difference stored into a float32 array
     const float r_cov = (float)c.r_cov, r_sns = (float)c.r_sns, r_comm = (float)c.r_comm;
@@ -146,17 +234,22 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         const float dl = (float)sqrt(dx * dx + dy * dy);
         w.d_u2g[p] = dl;
         // channel gain (common.py:45-55).  np: p_los stays float32 (python scalars are weak); np.square(h_ubs) is a
-        // float64 scalar, so d, fspl, pl and the gain are float64.
-        const float e = expf((float)(-c.chan_b) * (atanf((float)c.h_ubs / (dl + 1e-5f)) - (float)c.chan_a));
-        const float p_los = 1.0f / (1.0f + (float)c.chan_a * e);
-        const double d3 = sqrt((double)(dl * dl) + c.h_ubs * c.h_ubs);
-        const double q = c.c_fspl * d3 / 3e8;
-        const double fspl = q * q;
-        const double pl = (double)p_los * fspl * c.k_los + (double)(1.0f - p_los) * fspl * c.k_nlos;
-        const double g = 1.0 / pl;
+        // float64 scalar, so d, fspl, pl and the gain are float64.  Only needed where the link can carry signal or
+        // interference (d <= r_cov): p_itf and the served links are masked by it (:164,176,185).
+        float pitf = 0.f;
+        double g = 0.0;
+        if (dl <= r_cov) {
+            const float e = expf((float)(-c.chan_b) * (atanf((float)c.h_ubs / (dl + 1e-5f)) - (float)c.chan_a));
+            const float p_los = 1.0f / (1.0f + (float)c.chan_a * e);
+            const double d3 = sqrt((double)(dl * dl) + c.h_ubs * c.h_ubs);
+            const double q = c.c_fspl * d3 / 3e8;
+            const double fspl = q * q;
+            const double pl = (double)p_los * fspl * c.k_los + (double)(1.0f - p_los) * fspl * c.k_nlos;
+            g = 1.0 / pl;
+            pitf = (float)(c.p_tx * g);       // p_itf[i, :, rb] = p_tx * g[i] * mask_itf[i]  (:176): float64 -> float32
+        }
         w.gain[p] = g;
-        // p_itf[i, :, rb] = p_tx * g[i] * mask_itf[i]  (:176), float64 product stored into the float32 p_itf
-        w.pitf[p] = (dl <= r_cov) ? (float)(c.p_tx * g) : 0.0f;
+        w.pitf[p] = pitf;
     }
     for (int p = tid; p < U * U; p += nthr) {
         const int i = p / U, j = p - i * U;
@@ -164,27 +257,36 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         w.d_u2u[p] = (float)sqrt(dx * dx + dy * dy);
     }
     ctx.sync();
-    // nearest_ubs = np.argsort(d_u2g[:, m])  (:167): insertion sort (numpy's small-array path), ties by index
+    ctx.mark(2);
+    // nearest_ubs = np.argsort(d_u2g[:, m]) (:167) restricted to the UBSs that cover m (the loop over nearest_ubs can
+    // only pick those, :169): insertion sort = numpy's small-array path, ties by index
     for (int m = tid; m < G; m += nthr) {
         unsigned char* ord = w.order + (size_t)m * U;
+        int n = 0;
         for (int i = 0; i < U; ++i) {
             const float key = w.d_u2g[i * G + m];
-            int j = i;
+            if (!(key <= r_cov)) continue;
+            int j = n++;
             while (j > 0 && w.d_u2g[ord[j - 1] * G + m] > key) { ord[j] = ord[j - 1]; --j; }
             ord[j] = (unsigned char)i;
         }
+        w.ncov[m] = n;
     }
     ctx.sync();
+    ctx.mark(3);
 
     // ---- step 2: greedy RB scheduling in priority order (:166-178) — inherently sequential over GTs
+#if defined(__CUDA_ARCH__)
+    if (R <= 15 && U <= 16) {
+        if (tid < 32) sched_warp(c, w, tid);
+    } else
+#endif
     if (tid == 0) {
         for (int k = 0; k < G; ++k) {
             const int m = w.prior[k];
             const unsigned char* ord = w.order + (size_t)m * U;
-            for (int jj = 0; jj < U; ++jj) {
+            for (int jj = 0; jj < w.ncov[m]; ++jj) {
                 const int i = ord[jj];
-                const float dim = w.d_u2g[i * G + m];
-                if (!(dim <= r_cov)) break;                       // sorted by distance: nobody further covers m either
                 if (w.nsch[i] < R) {
                     int best = -1;
                     float bestv = 0.f;
@@ -204,48 +306,43 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         }
     }
     ctx.sync();
+    ctx.mark(4);
 
-    // ---- rates (:181-187)
+    // ---- rates (:181-187) and running averages (:193, np: float32 throughout; self.t is a weak python int)
     for (int m = tid; m < G; m += nthr) {
         float r = 0.f;
         const int i = w.sch_ubs[m];
         if (i >= 0) {
             const int rb = w.sch_rb[m];
-            float a[UBS_ENV_MAX_UBS];
-            for (int i2 = 0; i2 < U; ++i2) {
+            // p_itf[:, m, rb] with p_itf[i, m, rb] = 0 for the served GT (:177); np: (U,1) float32 copy .sum() -> pairwise
+            const float itf = np_sum_fn([&](int i2) {
                 const int oc = w.occ[i2 * R + rb];
-                a[i2] = (oc >= 0 && oc != m) ? w.pitf[i2 * G + m] : 0.f;       // p_itf[i, m, rb] = 0 for the served GT (:177)
-            }
-            const float itf = np_sum_f32(a, U);                                // np: (U,1) float32 copy .sum() -> pairwise
+                return (oc >= 0 && oc != m) ? w.pitf[i2 * G + m] : 0.f;
+            }, U);
             const double sinr = (c.p_tx * w.gain[i * G + m]) / ((double)itf + c.bw * c.n0);
             r = (float)(c.bw * log2(1.0 + sinr) * 1e-6);                       // np: float64, stored into float32
+            if (r != 0.f) w.deg[4 * U + i] = 1;                                // rate_per_ubs[i] != 0 (:188): UBS i is not idle
         }
         w.rate[m] = r;
-    }
-    ctx.sync();
-
-    // ---- step 3 (:193-199): running averages (np: float32 throughout; self.t is a weak python int)
-    for (int m = tid; m < G; m += nthr) {
-        const float a = (w.avg[m] * (float)t + w.rate[m]) / (float)(t + 1);
-        w.avg[m] = a;
-        const float x = a < 1e-6f ? 1e-6f : a;                                 // np.clip(x, 1e-6, inf)
+        const float av = (w.avg[m] * (float)t + r) / (float)(t + 1);
+        w.avg[m] = av;
+        const float x = av < 1e-6f ? 1e-6f : av;                               // np.clip(x, 1e-6, inf)
         w.tmp[m] = x;
         w.tmp2[m] = x * x;
+        // observation features that depend on the GT only (:237-240).  np: float32 / float64 -> float64
+        w.f_rate[m] = (float)((double)r / c.max_rate);
+        w.f_avg[m] = (float)((double)av / c.max_rate * (double)G / (double)(U * R));
     }
     ctx.sync();
-    if (tid == 0) {
-        const float s1 = np_sum_f32(w.tmp, G), s2 = np_sum_f32(w.tmp2, G);
-        const float fair = (s1 * s1) / ((float)G * s2);                        // compute_jain_fairness_index
-        const float rsum = np_sum_f32(w.rate, G);
-        const float mean = rsum / (float)G;                                    // np.mean of float32
-        const float gu = fair * mean;                                          // global_util
-        const float agu0 = is_reset ? 0.f : (float)info[3];
-        const float agu = (agu0 * (float)t + gu) / (float)(t + 1);
-        w.scal[S_FAIR] = fair;
-        w.scal[S_GU] = gu;
-        w.scal[S_MEAN] = mean;
-        w.scal[S_AGU] = agu;
-        w.scal[S_TPUT] = rsum * (float)c.dt / 1e3f;
+    ctx.mark(5);
+    // three pairwise sums (numpy order), one per warp on the device
+    {
+        // (the first warps are busy ranking the GTs below)
+        const int w0 = nthr >= 256 ? 96 : 0, w1 = nthr >= 256 ? 128 : (nthr >= 96 ? 32 : 0),
+                  w2 = nthr >= 256 ? 160 : (nthr >= 96 ? 64 : 0);
+        if (tid == w0) w.scal[5] = np_sum_f32(w.tmp, G);
+        if (tid == w1) w.scal[6] = np_sum_f32(w.tmp2, G);
+        if (tid == w2) w.scal[7] = np_sum_f32(w.rate, G);
     }
     // prior_gts = argsort(avg_rate_per_gt) (:199), ties by index: rank by counting
     for (int m = tid; m < G; m += nthr) {
@@ -257,66 +354,98 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         }
         st.prior[b * G + rank] = m;
     }
-    ctx.sync();
-
-    // ---- reward (:296-312), terminate (:314-316), collisions (:142-143)
-    const bool done = (t == c.episode_limit) && !is_reset;
-    if (tid < U || nthr == 1) {
-        for (int i = (nthr == 1 ? 0 : tid); i < U; i += (nthr == 1 ? 1 : U)) {
-            bool coll = false;
-            for (int j = 0; j < U; ++j) coll = coll || (j != i && (double)w.d_u2u[i * U + j] < c.safe_dist);
-            double rate_ubs = 0.0;                                             // rate_per_ubs (:188); only `== 0` is used
-            for (int m = 0; m < G; ++m) rate_ubs += (w.sch_ubs[m] == i) ? (double)w.rate[m] : 0.0;
-            // np: rew_scale * float32 stays float32, / max_rate (np.float64) promotes to float64
-            const float base = c.fair_service ? w.scal[S_GU] : w.scal[S_MEAN];
-            double lr = (double)((float)c.rew_scale * base) / c.max_rate;
-            lr = lr * (rate_ubs == 0.0 ? 0.0 : 1.0);
-            if (c.avoid_collision) lr = (coll ? 0.0 : 1.0) * lr - (coll ? 1.0 : 0.0) * c.penalty;
-            o.rew[b * U + i] = is_reset ? 0.f : (float)lr;
-            w.tmp[i] = is_reset ? 0.f : (float)lr;
-            w.nsch[i] = coll ? 1 : 0;                                          // reuse: collision flag
-            // own features (:223) + talk mask: bit i of mask[dst j] <=> d_u2u[i, j] <= r_comm  (env_wrappers.py:141-144)
-            o.x_agent[(b * U + i) * 2] = (float)(w.pos_u[i * 2] / c.range_pos);
-            o.x_agent[(b * U + i) * 2 + 1] = (float)(w.pos_u[i * 2 + 1] / c.range_pos);
-            uint32_t mk = 0;
-            for (int s = 0; s < U && s < 32; ++s) mk |= (w.d_u2u[s * U + i] <= r_comm) ? (1u << s) : 0u;
-            o.mask[b * U + i] = (int32_t)mk;
-            // per-agent compaction slots of visible GTs / UBSs (env_wrappers.py:71: rows with flag == 1, in order)
+    // per-agent compaction slots of visible GTs / UBSs (env_wrappers.py:71: rows with flag == 1, in order)
+#if defined(__CUDA_ARCH__)
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+        for (int i = wid; i < U; i += nw) {
             int cnt = 0;
-            for (int m = 0; m < G; ++m) w.slot[i * G + m] = (w.d_u2g[i * G + m] <= r_sns) ? cnt++ : -1;
-            w.deg[i] = cnt;
-            cnt = 0;
-            for (int j = 0; j < U; ++j) w.nslot[i * U + j] = (j != i && w.d_u2u[i * U + j] <= r_comm) ? cnt++ : -1;
-            w.deg[U + i] = cnt;
+            for (int m0 = 0; m0 < G; m0 += 32) {
+                const int m = m0 + lane;
+                const bool f = m < G && w.d_u2g[i * G + m] <= r_sns;
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if (m < G) w.slot[i * G + m] = f ? cnt + __popc(bal & ((1u << lane) - 1u)) : -1;
+                cnt += __popc(bal);
+            }
+            int cn = 0;
+            for (int j0 = 0; j0 < U; j0 += 32) {
+                const int j = j0 + lane;
+                const bool f = j < U && j != i && w.d_u2u[i * U + j] <= r_comm;
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if (j < U) w.nslot[i * U + j] = f ? cn + __popc(bal & ((1u << lane) - 1u)) : -1;
+                cn += __popc(bal);
+            }
+            if (lane == 0) { w.deg[i] = cnt; w.deg[U + i] = cn; }
         }
     }
+#else
+    for (int i = 0; i < U; ++i) {
+        int cnt = 0;
+        for (int m = 0; m < G; ++m) w.slot[i * G + m] = (w.d_u2g[i * G + m] <= r_sns) ? cnt++ : -1;
+        w.deg[i] = cnt;
+        cnt = 0;
+        for (int j = 0; j < U; ++j) w.nslot[i * U + j] = (j != i && w.d_u2u[i * U + j] <= r_comm) ? cnt++ : -1;
+        w.deg[U + i] = cnt;
+    }
+#endif
     ctx.sync();
+    ctx.mark(6);
+    // ---- reward (:296-312), terminate (:314-316), collisions (:142-143)
+    const bool done = (t == c.episode_limit) && !is_reset;
+    // fairness / utility (:195-198, np: float32), recomputed by every thread that needs them
+    const float s1 = w.scal[5], s2 = w.scal[6], rsum = w.scal[7];
+    const float fair = (s1 * s1) / ((float)G * s2);                            // compute_jain_fairness_index
+    const float mean = rsum / (float)G;                                        // np.mean of float32
+    const float gu = fair * mean;                                              // global_util
+    for (int i = tid; i < U; i += nthr) {
+        bool coll = false;
+        for (int j = 0; j < U; ++j) coll = coll || (j != i && (double)w.d_u2u[i * U + j] < c.safe_dist);
+        // np: rew_scale * float32 stays float32, / max_rate (np.float64) promotes to float64
+        const float base = c.fair_service ? gu : mean;
+        double lr = (double)((float)c.rew_scale * base) / c.max_rate;
+        lr = lr * (w.deg[4 * U + i] ? 1.0 : 0.0);                              // idle UBSs receive no reward (:305-306)
+        if (c.avoid_collision) lr = (coll ? 0.0 : 1.0) * lr - (coll ? 1.0 : 0.0) * c.penalty;
+        o.rew[b * U + i] = is_reset ? 0.f : (float)lr;
+        w.tmp[i] = is_reset ? 0.f : (float)lr;
+        w.nsch[i] = coll ? 1 : 0;                                              // reuse: collision flag
+        // own features (:223) + talk mask: bit i of mask[dst j] <=> d_u2u[i, j] <= r_comm  (env_wrappers.py:141-144)
+        o.x_agent[(b * U + i) * 2] = (float)(w.pos_u[i * 2] / c.range_pos);
+        o.x_agent[(b * U + i) * 2 + 1] = (float)(w.pos_u[i * 2 + 1] / c.range_pos);
+        uint32_t mk = 0;
+        for (int s = 0; s < U && s < 32; ++s) mk |= (w.d_u2u[s * U + i] <= r_comm) ? (1u << s) : 0u;
+        o.mask[b * U + i] = (int32_t)mk;
+    }
+    ctx.sync();
+    ctx.mark(8);
     if (tid == 0) {
         int a1 = 0, a2 = 0, ncoll = 0;
         double rmean = 0.0;
         for (int i = 0; i < U; ++i) {
             w.deg[2 * U + i] = a1;
             w.deg[3 * U + i] = a2;
+            o.off_seen[b * U + i] = a1;                                         // env-local exclusive prefix
+            o.off_near[b * U + i] = a2;
             a1 += w.deg[i];
             a2 += w.deg[U + i];
-            o.deg_seen[b * U + i] = w.deg[i];
-            o.deg_near[b * U + i] = w.deg[U + i];
             ncoll += w.nsch[i];
             rmean += (double)w.tmp[i];
         }
+        o.tot[2 * b] = a1;
+        o.tot[2 * b + 1] = a2;
         o.done[b] = done ? 1.f : 0.f;
         o.bad[b] = done ? 1.f : 0.f;                                            // BadMask: t == episode_limit (:122)
         st.t[b] = t;
-        info[0] = (is_reset ? 0.0 : info[0]) + rmean / U;                       // ep_ret
-        info[1] = (double)((is_reset ? 0.f : (float)info[1]) + w.scal[S_TPUT]); // total_throughput (np: float32)
-        info[2] = (is_reset ? 0.0 : info[2]) + ncoll / 2.0;                     // n_colls
-        info[3] = w.scal[S_AGU];
-        info[4] = w.scal[S_FAIR];
-        info[5] = w.scal[S_GU];
+        info[0] = inf0 + rmean / U;                                             // ep_ret
+        info[1] = (double)((float)inf1 + rsum * (float)c.dt / 1e3f);            // total_throughput (np: float32)
+        info[2] = inf2 + ncoll / 2.0;                                           // n_colls
+        info[3] = (double)(((float)inf3 * (float)t + gu) / (float)(t + 1));     // avg_global_util (np: float32)
+        info[4] = fair;
+        info[5] = gu;
         info[6] = t;
         info[7] = 0.0;
     }
     ctx.sync();
+    ctx.mark(9);
 
     // ---- persistent state + observation rows (:225-240), compacted per env into the staging area
     for (int i = tid; i < U * 2; i += nthr) st.pos_ubs[b * U * 2 + i] = w.pos_u[i];
@@ -327,7 +456,6 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         st.sched[(b * G + m) * 2 + 1] = w.sch_rb[m];
     }
     const double ngt = fmin(c.range_pos, c.r_sns), nub = fmin(c.range_pos, c.r_comm);
-    const double fair_scale_num = (double)G, fair_scale_den = (double)(U * R);
     for (int p = tid; p < U * G; p += nthr) {
         const int s = w.slot[p];
         if (s < 0) continue;
@@ -335,8 +463,8 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         float* row = o.stage_gt + (size_t)(w.deg[2 * U + i] + s) * Fg;
         row[0] = (float)(((double)w.pos_g[m * 2] - w.pos_u[i * 2]) / ngt);       // np: float32 - float64 -> float64
         row[1] = (float)(((double)w.pos_g[m * 2 + 1] - w.pos_u[i * 2 + 1]) / ngt);
-        row[2] = (float)((double)w.rate[m] / c.max_rate);
-        if (c.fair_service) row[3] = (float)((double)w.avg[m] / c.max_rate * fair_scale_num / fair_scale_den);
+        row[2] = w.f_rate[m];
+        if (c.fair_service) row[3] = w.f_avg[m];
     }
     for (int p = tid; p < U * U; p += nthr) {
         const int s = w.nslot[p];
@@ -351,15 +479,16 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
 // Scratch layout (words) shared by the step and pack kernels and the host harness.
 struct Scratch {
     UBS_HD static int64_t al(int64_t x) { return (x + 3) & ~(int64_t)3; }
-    int64_t off_deg_seen, off_deg_near, off_stage_gt, off_stage_ubs, words, gt_stride, ubs_stride;
+    int64_t off_off_seen, off_off_near, off_tot, off_stage_gt, off_stage_ubs, words, gt_stride, ubs_stride;
     UBS_HD Scratch(const ubs_env_cfg& c, int64_t B) {
         const int64_t N = B * c.n_ubs;
         const int Fg = c.fair_service ? 4 : 3;
         gt_stride = al((int64_t)c.n_ubs * c.n_gts * Fg);
         ubs_stride = al((int64_t)c.n_ubs * (c.n_ubs > 1 ? c.n_ubs - 1 : 1) * 2);
-        off_deg_seen = 0;
-        off_deg_near = al(N);
-        off_stage_gt = off_deg_near + al(N);
+        off_off_seen = 0;
+        off_off_near = al(N);
+        off_tot = off_off_near + al(N);
+        off_stage_gt = off_tot + al(2 * B);
         off_stage_ubs = off_stage_gt + B * gt_stride;
         words = off_stage_ubs + B * ubs_stride;
     }

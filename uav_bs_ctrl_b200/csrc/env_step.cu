@@ -9,14 +9,22 @@
 // (env_wrappers.py:65-89,137; algos/common.py:40-47) by pointer arithmetic, no graph objects.
 //
 // Compiled with -fmad=false (see Makefile): the env arithmetic must round like numpy's separate multiply / add.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "env_core.h"
 
 namespace ubs_env {
 
+__device__ long long g_phase_clock[32];   // UBS_ENV_PROFILE=1: clock64() of CTA 0 / thread 0 after every phase barrier
+
 struct DevCtx {
     int tid, nthr;
+    bool prof;
     __device__ void sync() const { __syncthreads(); }
+    __device__ void mark(int k) const {
+        if (prof && tid == 0 && k < 32) g_phase_clock[k] = clock64();
+    }
 };
 
 struct StepArgs {
@@ -26,10 +34,10 @@ struct StepArgs {
     const int64_t* actions;
     int32_t* scratch;
     int64_t B;
-    int is_reset;
+    int is_reset, profile;
 };
 
-__global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(256) env_step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ double smem_d[];
     const ubs_env_cfg& c = a.cfg;
     Work w;
@@ -44,66 +52,59 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ S
     o.bad = reinterpret_cast<float*>(a.pk.packet + a.pk.off_bad);
     o.stage_gt = reinterpret_cast<float*>(a.scratch + sc.off_stage_gt + b * sc.gt_stride);
     o.stage_ubs = reinterpret_cast<float*>(a.scratch + sc.off_stage_ubs + b * sc.ubs_stride);
-    o.deg_seen = a.scratch + sc.off_deg_seen;
-    o.deg_near = a.scratch + sc.off_deg_near;
-    DevCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    o.off_seen = a.scratch + sc.off_off_seen;
+    o.off_near = a.scratch + sc.off_off_near;
+    o.tot = a.scratch + sc.off_tot;
+    DevCtx ctx{(int)threadIdx.x, (int)blockDim.x, a.profile != 0 && blockIdx.x == 0};
+    ctx.mark(0);
     env_run(c, a.st, b, a.actions, a.is_reset != 0, w, o, ctx);
 }
 
-__device__ __forceinline__ int block_sum_128(int v, int* red) {
-    v = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    const int tot = red[0] + red[1] + red[2] + red[3];
-    __syncthreads();
-    return tot;
-}
-
 __global__ void __launch_bounds__(128) env_pack_kernel(const __grid_constant__ StepArgs a) {
-    __shared__ int red[4];
-    __shared__ int offs[2][UBS_ENV_MAX_UBS + 1];
+    __shared__ int red[2][4];
     const ubs_env_cfg& c = a.cfg;
     const Scratch sc(c, a.B);
     const int U = c.n_ubs, Fg = c.fair_service ? 4 : 3;
     const int64_t b = blockIdx.x, N = a.B * U;
-    const int32_t* deg_seen = a.scratch + sc.off_deg_seen;
-    const int32_t* deg_near = a.scratch + sc.off_deg_near;
+    const int32_t* tot = a.scratch + sc.off_tot;
+    // rows of all envs before this one: one pass over the per-env totals
     int s1 = 0, s2 = 0;
-    for (int64_t i = threadIdx.x; i < b * U; i += 128) { s1 += deg_seen[i]; s2 += deg_near[i]; }
-    const int base_seen = block_sum_128(s1, red);
-    const int base_near = block_sum_128(s2, red);
-    if (threadIdx.x == 0) {
-        int p1 = 0, p2 = 0;
-        for (int i = 0; i < U; ++i) {
-            offs[0][i] = p1; offs[1][i] = p2;
-            p1 += deg_seen[b * U + i]; p2 += deg_near[b * U + i];
-        }
-        offs[0][U] = p1; offs[1][U] = p2;
+    for (int64_t i = threadIdx.x; i < b; i += 128) { s1 += tot[2 * i]; s2 += tot[2 * i + 1]; }
+    s1 = __reduce_add_sync(0xffffffffu, s1);
+    s2 = __reduce_add_sync(0xffffffffu, s2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    const int my_seen = tot[2 * b], my_near = tot[2 * b + 1];
+    int o1 = 0, o2 = 0;
+    if (threadIdx.x < U) {
+        o1 = a.scratch[sc.off_off_seen + b * U + threadIdx.x];
+        o2 = a.scratch[sc.off_off_near + b * U + threadIdx.x];
     }
     __syncthreads();
+    const int base_seen = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    const int base_near = red[1][0] + red[1][1] + red[1][2] + red[1][3];
     int32_t* ip_seen = a.pk.packet + a.pk.off_ip_seen;
     int32_t* ip_near = a.pk.packet + a.pk.off_ip_near;
     if (threadIdx.x < U) {
-        ip_seen[b * U + threadIdx.x] = base_seen + offs[0][threadIdx.x];
-        ip_near[b * U + threadIdx.x] = base_near + offs[1][threadIdx.x];
+        ip_seen[b * U + threadIdx.x] = base_seen + o1;
+        ip_near[b * U + threadIdx.x] = base_near + o2;
     }
     if (b == a.B - 1 && threadIdx.x == 0) {
-        ip_seen[N] = base_seen + offs[0][U];
-        ip_near[N] = base_near + offs[1][U];
+        ip_seen[N] = base_seen + my_seen;
+        ip_near[N] = base_near + my_near;
     }
     const int32_t* sg = a.scratch + sc.off_stage_gt + b * sc.gt_stride;
     int32_t* xg = a.pk.packet + a.pk.off_x_gt + (int64_t)base_seen * Fg;
-    for (int i = threadIdx.x; i < offs[0][U] * Fg; i += 128) xg[i] = sg[i];
+    for (int i = threadIdx.x; i < my_seen * Fg; i += 128) xg[i] = sg[i];
     const int32_t* su = a.scratch + sc.off_stage_ubs + b * sc.ubs_stride;
     int32_t* xu = a.pk.packet + a.pk.off_x_ubs + (int64_t)base_near * 2;
-    for (int i = threadIdx.x; i < offs[1][U] * 2; i += 128) xu[i] = su[i];
+    for (int i = threadIdx.x; i < my_near * 2; i += 128) xu[i] = su[i];
 }
 
 static int check_cfg(const ubs_env_cfg* c, const char* fn) {
     using ubs::set_error;
     if (!c) { set_error("%s: NULL config", fn); return 2; }
     if (c->n_ubs < 1 || c->n_ubs > UBS_ENV_MAX_UBS) { set_error("%s: n_ubs must be in [1, %d] (got %d)", fn, UBS_ENV_MAX_UBS, c->n_ubs); return 2; }
-    if (c->n_gts < 1 || c->n_gts > 4096) { set_error("%s: n_gts must be in [1, 4096] (got %d)", fn, c->n_gts); return 2; }
+    if (c->n_gts < 1 || c->n_gts > 512) { set_error("%s: n_gts must be in [1, 512] (got %d)", fn, c->n_gts); return 2; }
     if (c->n_rbs < 1 || c->n_rbs > 64) { set_error("%s: n_rbs must be in [1, 64] (got %d)", fn, c->n_rbs); return 2; }
     if (c->n_actions < 1 || c->n_actions > UBS_ENV_MAX_ACTIONS) { set_error("%s: n_actions must be in [1, %d] (got %d)", fn, UBS_ENV_MAX_ACTIONS, c->n_actions); return 2; }
     if (!(c->range_pos > 0) || !(c->max_rate > 0)) { set_error("%s: range_pos / max_rate must be positive", fn); return 2; }
@@ -122,6 +123,7 @@ static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* s
     if (B == 0) return 0;
     StepArgs a;
     a.cfg = *cfg; a.st = *st; a.pk = *pk; a.actions = actions; a.scratch = scratch; a.B = B; a.is_reset = is_reset ? 1 : 0;
+    a.profile = getenv("UBS_ENV_PROFILE") != nullptr;
     const size_t smem = Work::bytes(cfg->n_ubs, cfg->n_gts, cfg->n_rbs);
     UBS_REQUIRE(smem <= 227 * 1024, "%s: env working set (%zu B) exceeds shared memory", fn, smem);
     static size_t attr_set = 0;
@@ -130,13 +132,21 @@ static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* s
         attr_set = smem;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    env_step_kernel<<<(unsigned)B, 128, smem, s>>>(a);
+    env_step_kernel<<<(unsigned)B, 256, smem, s>>>(a);
     if (int rc = ubs::check_launch(fn)) return rc;
     env_pack_kernel<<<(unsigned)B, 128, 0, s>>>(a);
     return ubs::check_launch(fn);
 }
 
 }  // namespace ubs_env
+
+// Diagnostic (tools/env_profile.py): cycle stamps of the last profiled ubs_env_step launch (UBS_ENV_PROFILE=1).
+extern "C" UBS_ENV_API int ubs_env_phase_clocks(int64_t* out32) {
+    long long h[32];
+    if (cudaMemcpyFromSymbol(h, ubs_env::g_phase_clock, sizeof(h)) != cudaSuccess) return 1;
+    for (int i = 0; i < 32; ++i) out32[i] = h[i];
+    return 0;
+}
 
 extern "C" UBS_ENV_API int64_t ubs_env_scratch_words(const ubs_env_cfg* cfg, int64_t B) {
     if (!cfg || B < 0) return -1;

@@ -123,6 +123,14 @@ UBS_API int ubs_gat_aggr_bwd(const float* el, const float* er, const float* res,
 UBS_API int ubs_tf32x3_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                     float* C, int64_t ldc, int64_t M, int N, int K, int relu, void* stream);
 
+/* Weight-gradient products of the window:  C[Mo, No] = A[R, Mo]^T . B[R, No]  (fp32 in / out, 3xTF32 on tcgen05,
+ * reduction over the R = T*N rows split into 256-row slices whose partial tiles are added by a second kernel in a
+ * fixed order).  Replaces the `grad_out.t() @ input` GEMMs autograd runs for nn.Linear / GRUCell weights.
+ * workspace: ubs_tf32x3_gemm_tn_workspace(R, Mo, No) floats, 16-byte aligned.  No multiple of 16, <= 128.          */
+UBS_API int64_t ubs_tf32x3_gemm_tn_workspace(int64_t R, int Mo, int No);
+UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                               float* workspace, int64_t R, int Mo, int No, void* stream);
+
 /* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
  * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
  * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.

@@ -43,3 +43,35 @@ def test_tf32x3_gemm_strided_views():
     ref = x.double() @ w.double().t()
     assert float((out[:, 64:128].double() - ref).abs().max() / ref.abs().max()) < 2e-6
     assert float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("R,Mo,No", [
+    (256, 128, 64),            # one slice, one tile
+    (300, 64, 16),             # ragged slice, Mo < one tile, narrowest No
+    (5000, 288, 64),           # [dW_ih_x; dW_vsq_x]: three Mo tiles, the last one ragged (32 rows)
+    (4099, 9, 64),             # dW_out: Mo = 9 (unaligned rows -> scalar loads)
+    (104448, 192, 64),         # exp3 window: dW_ih[:, H:]
+    (104448, 64, 128),         # exp3 window: dW_aggr
+    (20000, 130, 128),         # widest No, ragged Mo
+])
+def test_tf32x3_gemm_tn_is_fp32_accurate(R, Mo, No):
+    g = th.Generator().manual_seed(R + Mo + No)
+    a = th.randn(R, Mo, generator=g)
+    b = th.randn(R, No, generator=g)
+    ref64 = a.double().t() @ b.double()
+    ref32 = a.t() @ b
+    out = ops.tc_matmul_tn(a.to(DEV), b.to(DEV))
+    th.cuda.synchronize()
+    assert_as_accurate(out, ref32, ref64, what="3xTF32 gemm_tn", slack=4.0, floor_scale=2e-6)
+    out2 = ops.tc_matmul_tn(a.to(DEV), b.to(DEV))
+    assert th.equal(out, out2)                                   # fixed-order reduction of the slice partials
+
+
+def test_tf32x3_gemm_tn_strided_views():
+    g = th.Generator().manual_seed(1)
+    S = th.randn(6000, 480, generator=g).to(DEV)
+    x = th.randn(6000, 64, generator=g).to(DEV)
+    a = S[:, 192:480]                        # [dvsq | dgh] column block of the stash
+    out = ops.tc_matmul_tn(a, x)
+    ref = a.double().t() @ x.double()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-6

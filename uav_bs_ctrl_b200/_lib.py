@@ -40,6 +40,8 @@ _PROTOS = {
     "ubs_gat_aggr_bwd_workspace": (_i64, [_i64, _int, _int]),
     "ubs_gat_aggr_bwd": (C.c_int, [_F] * 15 + [_i64, _i64, _int, _int, _flt, _int, _ptr]),
     "ubs_tf32x3_gemm": (C.c_int, [_F, _i64, _F, _i64, _F, _F, _i64, _i64, _int, _int, _int, _ptr]),
+    "ubs_tf32x3_gemm_tn_workspace": (_i64, [_i64, _int, _int]),
+    "ubs_tf32x3_gemm_tn": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _F, _i64, _int, _int, _ptr]),
     "ubs_agent_seq2_smem_bytes": (_i64, [_int] * 6),
     "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _i64, _i64, _int, _ptr]),
     "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _i64, _int, _ptr]),

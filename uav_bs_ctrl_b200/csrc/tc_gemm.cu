@@ -246,6 +246,289 @@ __global__ void __launch_bounds__(NTHREADS, 1) tf32x3_gemm_kernel(const Args a) 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight-gradient products of the BPTT window:  C[Mo, No] = A[R, Mo]^T . B[R, No]   (R = T*N ~ 10^5 rows: the
+// REDUCTION dimension is the slow one of both operands).  Same 3xTF32 tcgen05 pipeline; the producers transpose while
+// they split: lane = row r of a 32-row chunk, so the 4-byte st.shared of one warp land in 32 different banks of the
+// K-major SWIZZLE_128B tile (K = r).  R is cut into slices of 256 rows (8 chunks = 32 accumulating MMAs per TMEM
+// accumulator, the same accumulation depth as the forward projections — the tensor core adds into fp32 with
+// truncation); every (128-row tile of Mo, slice) work item writes one partial tile and a second kernel adds the
+// partials in a fixed order (deterministic, round-to-nearest).
+constexpr int SLICE = 256;
+
+struct ArgsTN {
+    const float* A; const float* B; float* ws;
+    long long lda, ldb, R;
+    int Mo, No, stages, tmem_cols, nbuf, n_mtiles, a_vec, b_vec, depth, stage_stg_bytes;
+    long long n_items;
+};
+
+// 4 consecutive columns of one row, zero outside the matrix.  vec: rows are 16-byte aligned and ncols % 4 == 0, so a
+// float4 is either fully inside or fully outside; the load itself is unconditional (clamped address) so that all the
+// loads of a chunk are in flight together.
+__device__ __forceinline__ float4 load4(const float* base, long long row, long long ld, int col, int ncols, long long nrows, int vec) {
+    if (vec) {
+        const bool ok = row < nrows && col < ncols;
+        const long long r = row < nrows ? row : nrows - 1;
+        const int c = col < ncols ? col : 0;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * ld + c));
+        return ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const long long r = row < nrows ? row : nrows - 1;
+    const float* p = base + r * ld;
+    float4 v;
+    v.x = __ldg(p + (col < ncols ? col : 0));
+    v.y = __ldg(p + (col + 1 < ncols ? col + 1 : 0));
+    v.z = __ldg(p + (col + 2 < ncols ? col + 2 : 0));
+    v.w = __ldg(p + (col + 3 < ncols ? col + 3 : 0));
+    const bool okr = row < nrows;
+    v.x = (okr && col < ncols) ? v.x : 0.f;
+    v.y = (okr && col + 1 < ncols) ? v.y : 0.f;
+    v.z = (okr && col + 2 < ncols) ? v.z : 0.f;
+    v.w = (okr && col + 3 < ncols) ? v.w : 0.f;
+    return v;
+}
+
+// element (tile row m, k = r) of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void split_store_t(char* hi_tile, char* lo_tile, int m, int r, float x) {
+    const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float d = x - h;
+    const float l = __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xFFFFE000u);
+    const uint32_t off = sw128(m, r >> 2) + (uint32_t)((r & 3) << 2);
+    *reinterpret_cast<float*>(hi_tile + off) = h;
+    *reinterpret_cast<float*>(lo_tile + off) = l;
+}
+
+constexpr int TN_PROD_WARPS = 8, TN_THREADS = (TN_PROD_WARPS + 5) * 32;   // 8 producers | 4 epilogue | 1 MMA
+
+// Asynchronous copy of 4 consecutive columns of one row into a private 16-byte staging slot, zero-filled outside the
+// matrix (cp.async src-size 0): the global -> shared traffic of several chunks is in flight per thread without
+// holding registers.
+__device__ __forceinline__ void cp_async_row4(uint32_t dst, const float* base, long long row, long long ld, int col, int ncols,
+                                              long long nrows, int vec) {
+    const long long r = row < nrows ? row : nrows - 1;
+    if (vec) {
+        const int ok = (row < nrows && col < ncols) ? 16 : 0;
+        const float* src = base + r * ld + (col < ncols ? col : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok) : "memory");
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ok = (row < nrows && col + e < ncols) ? 4 : 0;
+            const float* src = base + r * ld + (col + e < ncols ? col + e : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * e), "l"(src), "r"(ok) : "memory");
+        }
+    }
+}
+
+// stage the (item, kc) chunk: slots [0,4) = this thread's A columns, [4, 4+nb4) = its B columns
+__device__ __forceinline__ void tn_stage(const ArgsTN& a, uint32_t stg, long long item, int kc, int warp, int lane, int nb4) {
+    const int mt = (int)(item % a.n_mtiles);
+    const long long row = (item / a.n_mtiles) * SLICE + kc * BK + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        cp_async_row4(stg + (uint32_t)(j * TN_PROD_WARPS * 32) * 16, a.A, row, a.lda, mt * BM + warp * 16 + 4 * j, a.Mo, a.R, a.a_vec);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (j < nb4)
+            cp_async_row4(stg + (uint32_t)((4 + j) * TN_PROD_WARPS * 32) * 16, a.B, row, a.ldb, 4 * (warp + TN_PROD_WARPS * j), a.No,
+                          a.R, a.b_vec);
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const ArgsTN a) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int No = a.No, S = a.stages;
+    constexpr int KC = SLICE / BK;                                  // chunks per work item
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t b_tile = (uint32_t)No * 128;
+    const uint32_t stage_bytes = 2 * BM * 128 + 2 * b_tile;        // {A hi, A lo, B hi, B lo}
+    char* sT = smem;
+    char* sStage = sT + (size_t)S * stage_bytes;                   // cp.async staging: depth x slots x 256 x 16 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + (size_t)a.depth * a.stage_stg_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, TN_PROD_WARPS * 32); mbar_init(empty + s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TN_PROD_WARPS + 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TN_PROD_WARPS) {
+        // ================================ producers (transposing split) ================================
+        // warp w: 16 columns of the A tile and every 8th float4 column of the B tile; lane = row of the chunk.
+        // cp.async keeps `depth` chunks in flight per thread in private staging slots (no registers held).
+        const int nb4 = (No / 4 - warp + TN_PROD_WARPS - 1) / TN_PROD_WARPS;          // <= 4 (No <= 128)
+        const int D = a.depth;                                                       // chunks in flight per thread
+        const long long my_items = a.n_items > blockIdx.x ? (a.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long long n_chunks = my_items * KC;
+        const uint32_t slots = 4 + (uint32_t)((No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS);
+        const uint32_t stg_stage = slots * TN_PROD_WARPS * 32 * 16;
+        const uint32_t stg0 = smem_u32(sStage) + (uint32_t)threadIdx.x * 16;
+        for (int g = 0; g < D; ++g) {                                                // prologue: D chunks in flight
+            if (g < n_chunks) tn_stage(a, stg0 + (uint32_t)g * stg_stage, blockIdx.x + (g / KC) * gridDim.x, g % KC, warp, lane, nb4);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (long long g = 0; g < n_chunks; ++g) {
+            const uint32_t it = (uint32_t)g;
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            // chunk g has landed once at most D-1 younger groups are pending
+            if (D == 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
+            else if (D == 5) asm volatile("cp.async.wait_group 4;" ::: "memory");
+            else if (D == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+            else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const char* stg = sStage + (size_t)(g % D) * stg_stage + (size_t)threadIdx.x * 16;
+            float4 xa[4], xb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xa[j] = *reinterpret_cast<const float4*>(stg + (size_t)(j * TN_PROD_WARPS * 32) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nb4) xb[j] = *reinterpret_cast<const float4*>(stg + (size_t)((4 + j) * TN_PROD_WARPS * 32) * 16);
+            // the slot is free again: refill it with chunk g + D
+            if (g + D < n_chunks)
+                tn_stage(a, stg0 + (uint32_t)(g % D) * stg_stage, blockIdx.x + ((g + D) / KC) * gridDim.x, (int)((g + D) % KC), warp, lane, nb4);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            mbar_wait(empty + s, ph ^ 1);
+            char* ahi = sT + (size_t)s * stage_bytes;
+            char* alo = ahi + BM * 128;
+            char* bhi = alo + BM * 128;
+            char* blo = bhi + b_tile;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = warp * 16 + 4 * j;
+                split_store_t(ahi, alo, m, lane, xa[j].x);
+                split_store_t(ahi, alo, m + 1, lane, xa[j].y);
+                split_store_t(ahi, alo, m + 2, lane, xa[j].z);
+                split_store_t(ahi, alo, m + 3, lane, xa[j].w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nb4) {
+                    const int n = 4 * (warp + TN_PROD_WARPS * j);
+                    split_store_t(bhi, blo, n, lane, xb[j].x);
+                    split_store_t(bhi, blo, n + 1, lane, xb[j].y);
+                    split_store_t(bhi, blo, n + 2, lane, xb[j].z);
+                    split_store_t(bhi, blo, n + 3, lane, xb[j].w);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full + s);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp == TN_PROD_WARPS + 4) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(No >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0, tc_ = 0;
+            for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x, ++tc_) {
+                const int acc = tc_ % a.nbuf;
+                mbar_wait(tempty + acc, ((tc_ / a.nbuf) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc * (uint32_t)(2 * No), dx = d + (uint32_t)No;
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const int s = it % S;
+                    mbar_wait(full + s, (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t ahi = smem_u32(sT + (size_t)s * stage_bytes), alo = ahi + BM * 128;
+                    const uint32_t bhi = alo + BM * 128, blo = bhi + b_tile;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t o = ks * 32;
+                        umma_tf32(d, make_desc(ahi + o), make_desc(bhi + o), idesc, (kc | ks) != 0);
+                        umma_tf32(dx, make_desc(ahi + o), make_desc(blo + o), idesc, (kc | ks) != 0);
+                        umma_tf32(dx, make_desc(alo + o), make_desc(bhi + o), idesc, 1);
+                    }
+                    umma_commit(empty + s);
+                }
+                umma_commit(tfull + acc);
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 8..11): partial tile -> workspace ================================
+        const int q = warp - TN_PROD_WARPS;            // == warp % 4: the TMEM lane quadrant this warp may read
+        uint32_t tc_ = 0;
+        for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x, ++tc_) {
+            const int acc = tc_ % a.nbuf;
+            mbar_wait(tfull + acc, (tc_ / a.nbuf) & 1);
+            tc_fence_after();
+            const int mt = (int)(item % a.n_mtiles);
+            const long long sl = item / a.n_mtiles;
+            const int m = mt * BM + q * 32 + lane;                  // row of C
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * No);
+            for (int c0 = 0; c0 < No; c0 += 16) {
+                uint32_t v[16], u[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                    : "r"(taddr + (uint32_t)(No + c0)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < a.Mo) {
+                    float* out = a.ws + ((size_t)sl * a.Mo + m) * No + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                        o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                        o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                        o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                        *reinterpret_cast<float4*>(out + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TN_PROD_WARPS + 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+    }
+}
+
+// C[m, n] = sum over slices of ws[sl, m, n], four interleaved accumulators combined in a fixed order
+__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ ws, long long n_slices, int P, int No,
+                                                        float* __restrict__ C, long long ldc) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    long long sl = 0;
+    for (; sl + 15 < n_slices; sl += 16) {              // 16 independent loads in flight per thread
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += ws[(sl + j) * P + i];
+    }
+    for (int j = 0; sl < n_slices; ++sl, ++j) acc[j] += ws[sl * P + i];
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int j = 0; j < w; ++j) acc[j] += acc[j + w];
+    C[(long long)(i / No) * ldc + (i % No)] = acc[0];
+}
+
 }  // namespace tc
 }  // namespace ubs
 
@@ -281,4 +564,49 @@ extern "C" UBS_API int ubs_tf32x3_gemm(const float* A, int64_t lda, const float*
     const int grid = (int)(n_tiles < ubs::kNumSMs ? n_tiles : ubs::kNumSMs);
     tf32x3_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
     return ubs::check_launch("ubs_tf32x3_gemm");
+}
+
+extern "C" UBS_API int64_t ubs_tf32x3_gemm_tn_workspace(int64_t R, int Mo, int No) {
+    const int64_t n_slices = (R + ubs::tc::SLICE - 1) / ubs::tc::SLICE;
+    return n_slices * (int64_t)Mo * No;
+}
+
+extern "C" UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                                          float* workspace, int64_t R, int Mo, int No, void* stream) {
+    using namespace ubs::tc;
+    UBS_REQUIRE(A && B && C && workspace && R >= 1, "ubs_tf32x3_gemm_tn: NULL argument");
+    UBS_REQUIRE(Mo >= 1 && lda >= Mo, "ubs_tf32x3_gemm_tn: bad Mo / lda");
+    UBS_REQUIRE(No >= 16 && No % 16 == 0 && No <= 128 && ldb >= No && ldc >= No, "ubs_tf32x3_gemm_tn: No must be a multiple of 16, <= 128 (got %d)", No);
+    UBS_REQUIRE(((uintptr_t)workspace % 16) == 0, "ubs_tf32x3_gemm_tn: workspace must be 16-byte aligned");
+    ArgsTN a{};
+    a.A = A; a.B = B; a.ws = workspace; a.lda = lda; a.ldb = ldb; a.R = R; a.Mo = Mo; a.No = No;
+    a.a_vec = (lda % 4 == 0 && Mo % 4 == 0 && ((uintptr_t)A % 16) == 0) ? 1 : 0;
+    a.b_vec = (ldb % 4 == 0 && ((uintptr_t)B % 16) == 0) ? 1 : 0;
+    a.n_mtiles = (Mo + BM - 1) / BM;
+    const long long n_slices = (R + SLICE - 1) / SLICE;
+    a.n_items = n_slices * a.n_mtiles;
+    const size_t stage_bytes = 2 * BM * 128 + 2 * (size_t)No * 128;           // UMMA operand tiles of one chunk
+    const size_t stg_bytes = (size_t)(4 + (No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS) * TN_PROD_WARPS * 32 * 16;
+    const size_t budget = 227 * 1024 - 256 - 1024;
+    const int stages = 2;                                                      // the MMAs of a chunk are short
+    int depth = (int)((budget - stages * stage_bytes) / stg_bytes);
+    if (depth > 6) depth = 6;
+    UBS_REQUIRE(depth >= 1, "ubs_tf32x3_gemm_tn: tiles do not fit shared memory");
+    a.stages = stages; a.depth = depth; a.stage_stg_bytes = (int)stg_bytes;
+    a.nbuf = 4 * No <= 512 ? 2 : 1;
+    int cols = 32;
+    while (cols < 2 * No * a.nbuf) cols *= 2;
+    a.tmem_cols = cols;
+    const size_t smem = stages * stage_bytes + depth * stg_bytes + 256 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(tf32x3_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int grid = (int)(a.n_items < ubs::kNumSMs ? a.n_items : ubs::kNumSMs);
+    tf32x3_gemm_tn_kernel<<<grid, TN_THREADS, smem, (cudaStream_t)stream>>>(a);
+    if (int rc = ubs::check_launch("ubs_tf32x3_gemm_tn")) return rc;
+    const int P = Mo * No;
+    tn_reduce_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, n_slices, P, No, C, ldc);
+    return ubs::check_launch("ubs_tf32x3_gemm_tn(reduce)");
 }

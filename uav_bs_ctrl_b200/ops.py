@@ -552,6 +552,41 @@ def tc_linear(x, w, bias=None, relu=False, out=None):
 
 
 USE_TC = True       # batched observation-side projections on the tensor cores (3xTF32); False: cuBLAS fp32
+USE_TC_TN = True    # weight-gradient products (A^T B over the T*N rows) on the tensor cores (3xTF32)
+_TN_WS = {}
+
+
+def tc_matmul_tn(a, b, out=None):
+    """``a.T @ b`` for ``a (R, Mo)``, ``b (R, No)`` (row-strided views allowed) with the reduction over the R rows on
+    the tensor cores (``ubs_tf32x3_gemm_tn``, 3xTF32: fp32-accurate, deterministic).  No autograd."""
+    lib = _lib.load()
+    _lib.require_cuda(a, b)
+    R, Mo = a.shape
+    No = b.shape[1]
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if b.stride(1) != 1:
+        b = b.contiguous()
+    if out is None:
+        out = th.empty(Mo, No, dtype=th.float32, device=a.device)
+    n = int(lib.ubs_tf32x3_gemm_tn_workspace(R, Mo, No))
+    key = (a.device, th.cuda.current_stream().cuda_stream)
+    ws = _TN_WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = th.empty(n, dtype=th.float32, device=a.device)
+        _TN_WS[key] = ws
+    with _timed("tf32x3_gemm_tn", (R, Mo, No)):
+        _lib.check(lib.ubs_tf32x3_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                          out.stride(0), ws.data_ptr(), R, Mo, No, _lib.stream()), "ubs_tf32x3_gemm_tn")
+    return out
+
+
+def matmul_tn(a, b):
+    """``a.T @ b``: the tcgen05 kernel for the long-reduction weight-gradient shapes, else the fp32 library GEMM."""
+    if USE_TC_TN and a.is_cuda and a.shape[0] >= 4096 and b.shape[1] % 16 == 0 and 16 <= b.shape[1] <= 128 \
+            and a.dtype == th.float32 and b.dtype == th.float32:
+        return tc_matmul_tn(a, b)
+    return a.t() @ b
 
 
 def dense(x, w, bias=None, relu=False):
@@ -702,13 +737,13 @@ class AgentSequence2(th.autograd.Function):
         Sx, Sh = S[:, :H3 + Vp], S[:, H3:]                          # [dgi | dvsq] and [dvsq | dgh]
         gb = S.sum(0)
         g = {"b_ih": gb[:H3], "b_hh": gb[H3 + Vp:]}
-        g["W_out"], g["b_out"] = dq2.t() @ h_out.view(TN, H), dq2.sum(0)
-        Gx = Sx.t() @ x                                             # (3H + Vp, H): [dW_ih[:, :H]; dW_vsq[:, :H]]
-        Gh = Sh.t() @ hprev                                         # (Vp + 3H, H): [dW_vsq[:, H:]; dW_hh]
+        g["W_out"], g["b_out"] = matmul_tn(dq2, h_out.view(TN, H)), dq2.sum(0)
+        Gx = matmul_tn(Sx, x)                                       # (3H + Vp, H): [dW_ih[:, :H]; dW_vsq[:, :H]]
+        Gh = matmul_tn(Sh, hprev)                                   # (Vp + 3H, H): [dW_vsq[:, H:]; dW_hh]
         g["W_hh"] = Gh[Vp:]
         dx = dense(Sx, W.Wdx_t)                                     # (TN, H) = [dgi | dvsq] @ [W_ih[:, :H]; W_vsq[:, :H]]
         if dims.tarmac:
-            g["W_ih"] = th.cat((Gx[:H3], S[:, :H3].t() @ sv_c.view(TN, M)), 1)
+            g["W_ih"] = th.cat((Gx[:H3], matmul_tn(S[:, :H3], sv_c.view(TN, M))), 1)
             gw = th.cat((Gx[H3:], Gh[:Vp]), 1)                      # (Vp, 2H)
             gbv = gb[H3:H3 + Vp]
             g["W_val"], g["b_val"] = gw[:M], gbv[:M]
@@ -719,7 +754,7 @@ class AgentSequence2(th.autograd.Function):
         if dims.aggr:
             dpre = dx.mul_(x > 0)
             xg2 = xg.view(TN, dims.Fin)
-            g["W_aggr"], g["b_aggr"] = dpre.t() @ xg2, dpre.sum(0)
+            g["W_aggr"], g["b_aggr"] = matmul_tn(dpre, xg2), dpre.sum(0)
             d_xg = dense(dpre, W.W_aggr_t).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         else:
             d_xg = dx.view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None

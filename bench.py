@@ -137,6 +137,10 @@ def train_cycle_arena(learner, arena, packets, T, eps, host_io, acts_host=None):
     learner.begin_sequence(arena)
     if host_io:
         arena.load(0, packets[0])
+    elif getattr(learner.args, "cuda_graphs", False) and not getattr(learner.args, "per_step_graphs", False):
+        # observations already resident: nothing on the host between the T act steps -> ONE graph for the window
+        learner.rollout_arena(None, arena, eps)
+        return learner.update_arena(arena, sync=False)
     for t in range(T):
         acts = learner.act_arena(arena, t, eps)
         if host_io:
@@ -224,6 +228,7 @@ def run_ours(a):
     use_arena = a.path == "arena"
     if use_arena:
         learner.args.cuda_graphs = not a.no_graphs
+        learner.args.per_step_graphs = a.per_step_graphs
         learner.policy_net.use_seq2_act = a.act_seq2
         layout, packets = make_packets(B, T, a.profile, seed=1234 + 100 * rank, pin=True)
         h2d = (T + 1) * layout.words * 4
@@ -326,8 +331,11 @@ def run_ours(a):
         for i in range(3):
             learner.begin_sequence(arena)
             ev[i][0].record()
-            for t in range(T):
-                learner.act_arena(arena, t, eps)
+            if learner.args.cuda_graphs and not a.per_step_graphs:
+                learner.rollout_arena(None, arena, eps)
+            else:
+                for t in range(T):
+                    learner.act_arena(arena, t, eps)
             ev[i][1].record()
             learner.update_arena(arena, sync=False)
             ev[i][2].record()
@@ -412,7 +420,8 @@ def run_ours(a):
                 "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, "
                                        f"{B} envs/GPU, T={T}, degree profile '{a.profile}'",
                            "env_steps_per_step": world * B * T, "update_batch": f"{B} sequences x {T} per GPU",
-                           "parallelism": f"dp{world}", "path": a.path + ("" if a.no_graphs or a.path != "arena" else "+cudagraphs"),
+                           "parallelism": f"dp{world}", "path": a.path + ("" if a.no_graphs or a.path != "arena" else
+                                             "+cudagraphs(per step)" if a.per_step_graphs else "+cudagraph(act window)"),
                            "l2_policy": "inputs exceed L2: "
                            f"{h2d / 2**20:.0f} MiB of observations are streamed per step (> 126 MB L2)"},
                 "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "e2e": e2e, "full_loop": full,
@@ -500,6 +509,8 @@ def main():
     ap.add_argument("--path", default="arena", choices=["arena", "graph"],
                     help="arena: packed packets + sequence arena (+ CUDA graphs); graph: reference-shaped graph objects")
     ap.add_argument("--no-graphs", action="store_true", help="arena path without CUDA-graph replay of the act step")
+    ap.add_argument("--per-step-graphs", action="store_true",
+                    help="value leg: one graph replay per vector-step (as the e2e leg must) instead of one per window")
     ap.add_argument("--act-seq2", action="store_true", help="act step through the resident-weight kernel (T=1) + small GEMMs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full-loop leg (device env in the loop)")

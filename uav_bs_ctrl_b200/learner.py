@@ -293,7 +293,9 @@ class MultiAgentQLearner:
         """One whole episode window on the device env (``envs.MultiUbsCoverageVecEnv``): for t in 0..T-1 the fused act
         step on slot t, then ``env.step`` writing observation / reward / done of slot t+1 — the reference's
         ``act -> env.step -> cache`` loop (``algos/madrqn/run.py:81-90``) with nothing returning to the host.  With
-        ``args.cuda_graphs`` all 5·T kernels are captured once per (arena, env) and replayed as ONE graph launch."""
+        ``args.cuda_graphs`` all 5·T kernels are captured once per (arena, env) and replayed as ONE graph launch.
+        ``env=None``: the T act steps alone, on observations that are already resident in the arena (replayed
+        episodes) — the same graph without the env kernels."""
         T = self.max_seq_len
         if not hasattr(self, "_eps_dev"):
             self._eps_dev = th.zeros((), device=self.device)
@@ -305,7 +307,8 @@ class MultiAgentQLearner:
         def run():
             for t in range(T):
                 self._act_arena_eager(arena, t)
-                env.step(arena, t)
+                if env is not None:
+                    env.step(arena, t)
 
         from . import ops
         if not getattr(self.args, "cuda_graphs", False) or ops.TIMER is not None:
@@ -315,14 +318,16 @@ class MultiAgentQLearner:
         g = self._act_graphs.get(key)
         if g is None:
             self.policy_net._packed(self.policy_net.arena_dims(arena), self.policy_net._fused_params())
-            snap = env.buf.snapshot()                    # the warm-up step below must not advance the episode
+            snap = env.buf.snapshot() if env is not None else None   # the warm-up step must not advance the episode
             side = th.cuda.Stream()
             side.wait_stream(th.cuda.current_stream())
             with th.cuda.stream(side):
                 self._act_arena_eager(arena, 0)          # warm-up outside capture (slot 1 is rewritten by the replay)
-                env.step(arena, 0)
+                if env is not None:
+                    env.step(arena, 0)
             th.cuda.current_stream().wait_stream(side)
-            env.buf.restore(snap)
+            if env is not None:
+                env.buf.restore(snap)
             g = th.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with th.cuda.graph(g):

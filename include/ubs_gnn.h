@@ -149,6 +149,15 @@ UBS_API int ubs_block_attn_bwd(const float* s, int64_t ld_s, const float* q, int
                        float* ds_work, int64_t n_nodes, int block, int key_size, int msg_size, float scale,
                        void* stream);
 
+/* ---- Mean aggregation over block-diagonal comm graphs (BaseComm / CommNet reduce step) ---------------------
+ * c_v = mean over the in-neighbours u of v of msg[u] (0 without in-edges): update_all(udf_msg, mailbox.mean(1)) of
+ * gnn_agents.py:125-133,144 / :205-214,224 for messages that depend on the source node only.  mask / block as in
+ * ubs_block_attn_fwd.  msg / out / grads are row-strided (ld_* in floats).  Deterministic (no atomics).        */
+UBS_API int ubs_block_mean_fwd(const float* msg, int64_t ld_msg, const uint32_t* mask, float* out, int64_t ld_out,
+                               int64_t n, int block, int F, void* stream);
+UBS_API int ubs_block_mean_bwd(const float* grad_out, int64_t ld_go, const uint32_t* mask, float* grad_msg, int64_t ld_gm,
+                               int64_t n, int block, int F, void* stream);
+
 /* ---- GRUCell gate math (nn.GRUCell, gate order r,z,n) given gi = W_ih x + b_ih, gh = W_hh h + b_hh --------- */
 UBS_API int ubs_gru_gates_fwd(const float* gi, const float* gh, const float* h, float* h_out, int64_t n, int H, void* stream);
 /* grad_gi, grad_gh: (n, 3H); grad_h_direct: (n, H) = grad_out * z (the part that does not go through W_hh). */

@@ -32,6 +32,8 @@ _PROTOS = {
     "ubs_block_attn_fwd": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _U, _F, _F, _i64, _int, _int, _int, _flt, _ptr]),
     "ubs_block_attn_bwd": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _U, _F, _F, _F, _i64, _F, _i64, _F, _i64, _F,
                                      _i64, _int, _int, _int, _flt, _ptr]),
+    "ubs_block_mean_fwd": (C.c_int, [_F, _i64, _U, _F, _i64, _i64, _int, _int, _ptr]),
+    "ubs_block_mean_bwd": (C.c_int, [_F, _i64, _U, _F, _i64, _i64, _int, _int, _ptr]),
     "ubs_gru_gates_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),

@@ -160,6 +160,17 @@ class GraphObservationEncoder(nn.Module):
 
 
 # ============================================================================================== comm protocols
+def _mean_of_sources(g, per_node_msg):
+    """Mean over in-edges of a message that depends on the source node only (BaseComm / CommNet).  Batched per-env
+    comm graphs on the GPU go through the block-mean kernel (no edge list); anything else through torch ops."""
+    blk = g.block_mask() if per_node_msg.is_cuda else None
+    if blk is not None:
+        block, mask = blk
+        return ops.BlockMean.apply(per_node_msg, mask, block)
+    src, _ = g.edges()
+    return _mean_by_dst(g, per_node_msg.index_select(0, src), per_node_msg.shape[0])
+
+
 def _mean_by_dst(g, msg, n):
     _, dst = g.edges()
     out = th.zeros((n,) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device).index_add_(0, dst, msg)
@@ -211,8 +222,7 @@ class BaseComm(nn.Module):
         if g.number_of_edges() == 0:
             c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
         else:
-            src, _ = g.edges()
-            c = _mean_by_dst(g, self.f_msg(th.cat((x, h.detach()), 1)).index_select(0, src), x.shape[0])
+            c = _mean_of_sources(g, self.f_msg(th.cat((x, h.detach()), 1)))
         return self.f_udt(th.cat((x, c), 1), h)
 
 
@@ -256,8 +266,7 @@ class CommNet(nn.Module):
             if g.number_of_edges() == 0:
                 c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
             else:
-                src, _ = g.edges()
-                c = _mean_by_dst(g, h.detach().index_select(0, src), x.shape[0])
+                c = _mean_of_sources(g, h.detach())
             h = self.f_mod(x + self.c_mod(c), h)
         return h
 

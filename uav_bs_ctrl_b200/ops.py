@@ -236,6 +236,39 @@ class BlockAttention(th.autograd.Function):
         return g, None, None, None, None, None
 
 
+class BlockMean(th.autograd.Function):
+    """``c_v = mean_{u -> v} msg[u]`` over a block-diagonal comm graph (``ubs_block_mean_fwd / bwd``): the reduce step of
+    BaseComm / CommNet.  ``msg (N, F)``, ``mask (N,) int32`` bit patterns, ``block`` = agents per env."""
+
+    @staticmethod
+    def forward(ctx, msg, mask, block):
+        _lib.require_cuda(msg, mask)
+        lib = _lib.load()
+        msg = _f32c(msg)
+        N, F_ = msg.shape
+        if mask.dtype not in (th.int32, th.uint32) or mask.numel() != N:
+            raise TypeError("mask must be int32 (bit pattern of uint32) with one entry per node")
+        out = th.empty(N, F_, dtype=th.float32, device=msg.device)
+        with _timed("block_mean_fwd", (N, block, F_)):
+            _lib.check(lib.ubs_block_mean_fwd(msg.data_ptr(), F_, _lib.ptr(mask), out.data_ptr(), F_, N, block, F_,
+                                              _lib.stream()), "ubs_block_mean_fwd")
+        ctx.save_for_backward(mask)
+        ctx.block = block
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (mask,) = ctx.saved_tensors
+        lib = _lib.load()
+        grad_out = _f32c(grad_out)
+        N, F_ = grad_out.shape
+        g = th.empty_like(grad_out)
+        with _timed("block_mean_bwd", (N, ctx.block, F_)):
+            _lib.check(lib.ubs_block_mean_bwd(grad_out.data_ptr(), F_, _lib.ptr(mask), g.data_ptr(), F_, N, ctx.block, F_,
+                                              _lib.stream()), "ubs_block_mean_bwd")
+        return g, None, None
+
+
 class GRUGates(th.autograd.Function):
     """``nn.GRUCell`` gate math on precomputed projections ``gi (N,3H)``, ``gh (N,3H)`` and ``h (N,H)``."""
 

@@ -55,8 +55,12 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, size_t row
 // EPL = edges per lane per pass: the weight / destination operands of a channel (one LDS.128 + one LDS.64) are reused
 // for EPL edges, which moves the loop from shared-memory-issue bound (2 LDS : 5 FFMA) towards FFMA bound.  A lane
 // still visits its edges in the same order (beg+li, +GS, +2GS, ...), so the result is bit-identical for every EPL.
-template <int FS, int HEADS, int GS, int EPL>
+// HS = head split: a destination is HS work items, each owning HEADS / HS heads (heads are independent: own softmax,
+// own output channels), so a launch that cannot fill the SMs (the act step: 2 048 destinations) gets HS x the warps,
+// each with 1 / HS of the channel loop.  Results are bit-identical for every HS.
+template <int FS, int HEADS, int GS, int EPL, int HS>
 __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
+    constexpr int HPW = HEADS / HS;        // heads per work item
     constexpr int GPW = 32 / GS;           // destination groups per warp
     constexpr int GPB = 256 / GS;          // groups per block
     const int D = a.D, H = HEADS * D;
@@ -114,9 +118,11 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
     const float slope = a.slope;
     const bool relu = a.flags & UBS_GAT_RELU, has_res = a.flags & UBS_GAT_RESIDUAL;
 
-    for (int base = warp_first; base < a.n_dst; base += stride) {
-        const int v = base + (tid % 32) / GS;
-        const bool active = v < a.n_dst;
+    const int n_items = a.n_dst * HS;
+    for (int base = warp_first; base < n_items; base += stride) {
+        const int item = base + (tid % 32) / GS;
+        const int v = item / HS, k0 = (item - v * HS) * HPW;       // destination, first head of this work item
+        const bool active = item < n_items;
         int beg = 0, end = 0;
         float xv0 = 0.f, xv1 = 0.f;
         const int seg = active ? v / a.n_dst_seg : 0;
@@ -132,18 +138,19 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
             xv1 = a.F_d > 1 ? __ldg(xd + 1) : 0.f;
         }
         // destination part of the score pre-activation, shared by all edges of v
-        for (int ch = li; ch < H; ch += GS) {
+        for (int ch = k0 * D + li; ch < (k0 + HPW) * D; ch += GS) {
             const float4 w = wD[ch];
             cbuf[ch] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
         }
         __syncwarp();
-        float lin[HEADS];
+        float lin[HPW];
 #pragma unroll
-        for (int k = 0; k < HEADS; ++k) lin[k] = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
+        for (int k = 0; k < HPW; ++k)
+            lin[k] = fmaf(hP[(k0 + k) * 8 + 5], xv1, fmaf(hP[(k0 + k) * 8 + 4], xv0, hP[(k0 + k) * 8 + 6]));
 
-        float m[HEADS], l[HEADS], acc[HEADS][FS];
+        float m[HPW], l[HPW], acc[HPW][FS];
 #pragma unroll
-        for (int k = 0; k < HEADS; ++k) {
+        for (int k = 0; k < HPW; ++k) {
             m[k] = -CUDART_INF_F; l[k] = 0.f;
 #pragma unroll
             for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
@@ -164,11 +171,11 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < HEADS; ++k) {
-                const float4* wk = wA + k * D;
-                const float2* ck = cbuf + k * D;
+            for (int k = 0; k < HPW; ++k) {
+                const float4* wk = wA + (k0 + k) * D;
+                const float2* ck = cbuf + (k0 + k) * D;
                 // linear part of the score: (1+s)/2 * attn_k . (W_src x + W_dst x_v + b)
-                const float4 pk = *reinterpret_cast<const float4*>(hP + k * 8);
+                const float4 pk = *reinterpret_cast<const float4*>(hP + (k0 + k) * 8);
                 float s[EPL];
 #pragma unroll
                 for (int j = 0; j < EPL; ++j) {
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
         }
         // merge the per-lane online-softmax states of the group
 #pragma unroll
-        for (int k = 0; k < HEADS; ++k) {
+        for (int k = 0; k < HPW; ++k) {
             const float M = group_max<GS>(m[k]);
             const float sc = (m[k] == -CUDART_INF_F) ? 0.f : __expf(m[k] - M);
             l[k] = group_sum<GS>(l[k] * sc);
@@ -217,10 +224,10 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
         }
         if (active) {
 #pragma unroll
-            for (int k = 0; k < HEADS; ++k) {
+            for (int k = 0; k < HPW; ++k) {
                 const float inv = l[k] > 0.f ? 1.0f / l[k] : 0.f;
                 for (int d = li; d < D; d += GS) {
-                    const int ch = k * D + d;
+                    const int ch = (k0 + k) * D + d;
                     const float4 w = wA[ch];
                     const float4 r = wR[ch];
                     float o = 0.f;
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
                     a.out[(size_t)v * a.ld_out + ch] = o;
                 }
                 if (li == 0 && a.smax != nullptr) {
-                    a.smax[(size_t)v * HEADS + k] = l[k] > 0.f ? m[k] : 0.f;
-                    a.ssum[(size_t)v * HEADS + k] = l[k];
+                    a.smax[(size_t)v * HEADS + k0 + k] = l[k] > 0.f ? m[k] : 0.f;
+                    a.ssum[(size_t)v * HEADS + k0 + k] = l[k];
                 }
             }
         }
@@ -482,19 +489,29 @@ static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
     if (epl == 2 && gs > 8 && nd * (gs / 2) / 32 >= (int64_t)kNumSMs * 8 && n_edges <= 96 * nd) gs /= 2;
     if (const char* ev = getenv("UBS_GAT_GS")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) gs = v; }
     if (const char* ev = getenv("UBS_GAT_EPL")) { const int v = atoi(ev); if (v == 1 || v == 2) epl = v; }
+    // head split for launches that cannot fill the SMs even with 32 lanes per destination (the act step)
+    int hs = (HEADS % 2 == 0 && gs == 32 && nd < (int64_t)kNumSMs * 32) ? 2 : 1;
+    if (const char* ev = getenv("UBS_GAT_HS")) { const int v = atoi(ev); if (v == 1 || (v == 2 && HEADS % 2 == 0 && gs == 32)) hs = v; }
     const int gpb = 256 / gs;
-    int64_t need = ((int64_t)a.n_dst + gpb - 1) / gpb;
+    int64_t need = ((int64_t)a.n_dst * hs + gpb - 1) / gpb;
     int64_t cap = (int64_t)kNumSMs * 4;                            // persistent: up to 4 resident CTAs per SM
     const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
     const size_t smem = (size_t)H * 3 * sizeof(float4) + (size_t)gpb * (2 * H + 2) * sizeof(float) + HEADS * 8 * sizeof(float);
+    if constexpr (HEADS % 2 == 0) {
+        if (hs == 2) {
+            if (epl == 2) gatv2_fwd_kernel<FS, HEADS, 32, 2, 2><<<grid, 256, smem, st>>>(a);
+            else gatv2_fwd_kernel<FS, HEADS, 32, 1, 2><<<grid, 256, smem, st>>>(a);
+            return check_launch("ubs_gatv2_fwd");
+        }
+    }
     if (epl == 2) {
-        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 2><<<grid, 256, smem, st>>>(a);
-        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 2><<<grid, 256, smem, st>>>(a);
-        else gatv2_fwd_kernel<FS, HEADS, 32, 2><<<grid, 256, smem, st>>>(a);
+        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 2, 1><<<grid, 256, smem, st>>>(a);
+        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 2, 1><<<grid, 256, smem, st>>>(a);
+        else gatv2_fwd_kernel<FS, HEADS, 32, 2, 1><<<grid, 256, smem, st>>>(a);
     } else {
-        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 1><<<grid, 256, smem, st>>>(a);
-        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 1><<<grid, 256, smem, st>>>(a);
-        else gatv2_fwd_kernel<FS, HEADS, 32, 1><<<grid, 256, smem, st>>>(a);
+        if (gs == 8) gatv2_fwd_kernel<FS, HEADS, 8, 1, 1><<<grid, 256, smem, st>>>(a);
+        else if (gs == 16) gatv2_fwd_kernel<FS, HEADS, 16, 1, 1><<<grid, 256, smem, st>>>(a);
+        else gatv2_fwd_kernel<FS, HEADS, 32, 1, 1><<<grid, 256, smem, st>>>(a);
     }
     return check_launch("ubs_gatv2_fwd");
 }

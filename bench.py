@@ -321,6 +321,8 @@ def run_ours(a):
                 "env": f"device-resident MultiUbsCoverageEnv, DenseHotSpot {U} UBS x {G} GT (maps.py:83-113), "
                        f"episode_limit {T}, eps-greedy {eps}; resets from a pool of {len(pool)} x {B} RNG-matched layouts; "
                        "one CUDA graph per rollout" + ("" if learner.args.cuda_graphs else " (graphs off)")}
+        if rank == 0 and world == 1 and not a.no_cpu:
+            full["cpu_env_port"] = cpu_env_port(m, B)
         for t in range(T + 1):                            # the value / roofline passes below replay the synthetic episode
             arena.load(t, packets[t])
 
@@ -475,6 +477,35 @@ def cpu_reference(B, T, profile, steps, warmup, seed=1234):
     return {"value": B * T * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{steps} cycle(s) of {B} envs x T={T} steps (act x T + one BPTT update), torch CPU oracle, "
                       f"{cores} threads, {dt:.1f} s", "seconds": dt}
+
+
+def cpu_env_port(m, B, steps=20):
+    """The device env's CPU counterpart, timed on one host core: the serial host build of the SAME env core
+    (oracle/env_host.cpp — test infrastructure; the reference's numpy env itself cannot travel to the GPU box, its
+    measured rate in the build container is 150 env-steps/s per core at 8 x 80)."""
+    import ctypes as C
+    import numpy as np
+    from uav_bs_ctrl_b200 import envs as E
+    from uav_bs_ctrl_b200.arena import PacketLayout
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libubs_env_host.so"))
+    lib.ubs_env_host_step.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int]
+    lib.ubs_env_host_scratch_words.restype = C.c_int64
+    lib.ubs_env_host_scratch_words.argtypes = [C.c_void_p, C.c_int64]
+    cfg = E.make_cfg(m)
+    buf = E.EnvBuffers(cfg, B, "cpu", lib.ubs_env_host_scratch_words(C.byref(cfg), B))
+    buf.set_layout(*E.sample_layouts(m, range(B)))
+    L = PacketLayout(B, cfg.n_ubs, cfg.n_gts)
+    pkt = th.zeros(L.words, dtype=th.int32)
+    st, pk = buf.state_struct(), E.packet_struct(L, pkt)
+    lib.ubs_env_host_step(C.byref(cfg), C.byref(st), None, C.byref(pk), buf.scratch.data_ptr(), B, 1)
+    acts = th.as_tensor(np.random.RandomState(0).randint(0, cfg.n_actions, size=(steps, B * cfg.n_ubs)), dtype=th.int64)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        lib.ubs_env_host_step(C.byref(cfg), C.byref(st), acts[k].data_ptr(), C.byref(pk), buf.scratch.data_ptr(), B, 0)
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{steps} steps of {B} env instances, serial C++ build of the env core, {dt:.2f} s"}
 
 
 def run_reference(a):

@@ -457,7 +457,7 @@ _SIDE_STREAMS = {}
 def _side_stream(dev, i):
     key = (dev.index, i)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = th.cuda.Stream(device=dev)
+        _SIDE_STREAMS[key] = th.cuda.Stream(device=dev, priority=-1)     # high priority: the short relation goes first
     return _SIDE_STREAMS[key]
 
 
@@ -497,7 +497,12 @@ class SegmentEncode(th.autograd.Function):
         # small launches (the act step) cannot fill the chip: relations run side by side on a forked stream
         fork = R > 1 and rows <= 8192 and TIMER is None
         cur = th.cuda.current_stream()
-        for r, sp in enumerate(specs):
+        # forked: the side-stream relations (short: `near`) are enqueued first on a high-priority stream so that their
+        # CTAs are resident next to the long relation's instead of queueing behind them
+        order = (list(range(1, R)) + [0]) if fork else list(range(R))
+        sides = []
+        for r in order:
+            sp = specs[r]
             W = ps[7 * r:7 * r + 7]
             side = _side_stream(dev, r) if (fork and r > 0) else None
             if side is not None:
@@ -511,7 +516,9 @@ class SegmentEncode(th.autograd.Function):
                     sp.st_ip, sp.st_sidx, R * H, sp.F_s, F_d, heads, D, float(slope), int(flags), _lib.stream()),
                     "ubs_gatv2_seg_fwd")
             if side is not None:
-                cur.wait_stream(side)
+                sides.append(side)
+        for side in sides:
+            cur.wait_stream(side)
         if need_grad:
             ctx.save_for_backward(keepalive, out, stats, *[p for p in ps if p is not None])
             ctx.cfg = (specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, float(slope), int(flags),

@@ -39,7 +39,8 @@ extern "C" {
 /* Static parameters of a map + env (maps.py:7-34, mubs_cov.py:13-66); every derived constant is computed by the host
  * with the reference's own expression so that it is bit-identical (uav_bs_ctrl_b200/envs.py). */
 typedef struct {
-    int32_t n_ubs, n_gts, n_rbs, n_actions, episode_limit, fair_service, avoid_collision, reserved;
+    int32_t n_ubs, n_gts, n_rbs, n_actions, episode_limit, fair_service, avoid_collision;
+    int32_t gts_f64; /* the map returns float64 GT positions (HotSpot, Map, DenseHotSpotV2): get_state divides in float64 */
     double range_pos, r_cov, r_sns, r_comm; /* metres; r_sns / r_comm may be +inf */
     double dt, rew_scale;                   /* maps.py: dt, reward_scale_rate */
     double h_ubs, p_tx, n0, bw;             /* mubs_cov.py:14-17 */
@@ -66,6 +67,7 @@ typedef struct {
 typedef struct {
     int32_t* packet;
     int64_t off_x_gt, off_x_ubs, off_x_agent, off_ip_seen, off_ip_near, off_mask, off_rew, off_done, off_bad;
+    int64_t off_state; /* (B, 2U + (3 + fair_service) G) global state of get_state() (mubs_cov.py:244-262) for QMIX; -1: not stored */
 } ubs_env_packet;
 
 /* Words of device scratch ubs_env_step / ubs_env_reset need for B envs (staging of the per-env compacted rows). */

@@ -60,7 +60,8 @@ class HostEnv:
     def __init__(self, cfg, B=1):
         self.lib, self.cfg, self.B = _host_lib(), cfg, B
         self.buf = E.EnvBuffers(cfg, B, "cpu", self.lib.ubs_env_host_scratch_words(C.byref(cfg), B))
-        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, 4 if cfg.fair_service else 3, 2)
+        fg = 4 if cfg.fair_service else 3
+        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts)
         self.packet = th.zeros(self.layout.words, dtype=th.int32)
 
     def run(self, actions=None):
@@ -79,7 +80,8 @@ class DevEnv:
         from uav_bs_ctrl_b200 import _lib
         self._lib, self.lib, self.cfg, self.B = _lib, _lib.load(), cfg, B
         self.buf = E.EnvBuffers(cfg, B, "cuda", self.lib.ubs_env_scratch_words(C.byref(cfg), B))
-        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, 4 if cfg.fair_service else 3, 2)
+        fg = 4 if cfg.fair_service else 3
+        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts)
         self.packet = th.zeros(self.layout.words, dtype=th.int32, device="cuda")
 
     def run(self, actions=None):
@@ -176,6 +178,8 @@ def check_snapshot(env, e, k, b=0, check_prior=True):
         ref_mask[d] |= 1 << int(s)
     assert np.array_equal(mask, ref_mask), f"step {k}: talk mask"
     close(L.section(pkt, "rew").numpy()[b * U:(b + 1) * U], e["reward"][k], f"step {k}: reward", scale=1.0)
+    sd = L.state_dim                                          # get_state() -> the QMIX mixer's input
+    close(L.section(pkt, "state").numpy()[b * sd:(b + 1) * sd], e["state"][k], f"step {k}: global state", scale=1.0)
     assert float(L.section(pkt, "done")[b]) == float(e["done"][k]) and float(L.section(pkt, "bad")[b]) == float(e["bad"][k])
 
 

@@ -3,6 +3,7 @@ from .gnn_agents import (GATv2Conv, GRUCell, GraphObservationEncoder, DenseObser
                          DiscreteComm, CommNet, EdgeConv, GnnAgent, DrqnGnnAgent)
 from .rnn_agents import RnnAgent
 from .dueling import DuelingLayer
+from .mixers import QMixer
 
 REGISTRY = {"rnn": RnnAgent, "gnn": GnnAgent}            # MADRQN
 DRQN_REGISTRY = {"rnn": RnnAgent, "gnn": DrqnGnnAgent}   # DRQN

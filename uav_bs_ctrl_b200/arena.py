@@ -33,15 +33,18 @@ def _al4(n: int) -> int:
 class PacketLayout:
     """Word offsets of the sections of one observation packet for ``B`` envs × ``U`` agents × ``G`` ground terminals."""
 
-    FLOAT = ("x_gt", "x_ubs", "x_agent", "rew", "done", "bad")
+    FLOAT = ("x_gt", "x_ubs", "x_agent", "rew", "done", "bad", "state")
 
-    def __init__(self, B: int, U: int, G: int, F_ag: int = 2, F_gt: int = 4, F_ubs: int = 2):
+    def __init__(self, B: int, U: int, G: int, F_ag: int = 2, F_gt: int = 4, F_ubs: int = 2, state_dim: int = 0):
         self.B, self.U, self.G, self.N = B, U, G, B * U
         self.F_ag, self.F_gt, self.F_ubs = F_ag, F_gt, F_ubs
         N = self.N
         self.cap_gt, self.cap_ubs = N * G, N * max(U - 1, 0)
         sizes = [("x_gt", self.cap_gt * F_gt), ("x_ubs", self.cap_ubs * F_ubs), ("x_agent", N * F_ag),
                  ("ip_seen", N + 1), ("ip_near", N + 1), ("mask", N), ("rew", N), ("done", B), ("bad", B)]
+        self.state_dim = state_dim                                   # global env state (QMIX), optional last section
+        if state_dim:
+            sizes.append(("state", B * state_dim))
         self.off: Dict[str, int] = {}
         self.size: Dict[str, int] = {}
         o = 0
@@ -56,7 +59,7 @@ class PacketLayout:
         return v.view(th.float32) if name in self.FLOAT else v
 
     def key(self):
-        return (self.B, self.U, self.G, self.F_ag, self.F_gt, self.F_ubs)
+        return (self.B, self.U, self.G, self.F_ag, self.F_gt, self.F_ubs, self.state_dim)
 
 
 class ObsPacket:
@@ -73,7 +76,7 @@ class ObsPacket:
     def sec(self, name):
         return self.layout.section(self.buf, name)
 
-    def fill_from_dense(self, agent_obs, gt_obs, ubs_obs, comm_adj=None, rew=None, done=None, bad=None):
+    def fill_from_dense(self, agent_obs, gt_obs, ubs_obs, comm_adj=None, rew=None, done=None, bad=None, state=None):
         """Dense env observations (``envs/mubs_cov/mubs_cov.py:215-242`` format, see ``builder.py``) → packet."""
         L = self.layout
         B, U, N = L.B, L.U, L.N
@@ -103,6 +106,8 @@ class ObsPacket:
         self.sec("rew")[:] = 0 if rew is None else rew.reshape(-1).float()
         self.sec("done")[:] = 0 if done is None else done.reshape(-1).float()
         self.sec("bad")[:] = 0 if bad is None else bad.reshape(-1).float()
+        if L.state_dim:
+            self.sec("state")[:] = 0 if state is None else state.reshape(-1).float()
         return self
 
     def to_graph(self) -> HeteroGraph:
@@ -170,6 +175,12 @@ class SequenceArena:
     def rewards(self, T: int) -> th.Tensor:
         """``(T, B, U)`` rewards of transitions 0..T-1 (stored with observations 1..T)."""
         return self.sec("rew")[1:T + 1].reshape(T, self.layout.B, self.layout.U)
+
+    def states(self, T: int) -> th.Tensor:
+        """``(T, B, state_dim)`` global states of slots 0..T-1 (QMIX)."""
+        if not self.layout.state_dim:
+            raise ValueError("this arena was created without a state section (PacketLayout(state_dim=...))")
+        return self.sec("state")[:T].reshape(T, self.layout.B, self.layout.state_dim)
 
     def dones(self, T: int) -> th.Tensor:
         """``(T, B, 1)``: ``(1 - bad_mask) * done`` (reference ``learner.py:91``)."""

@@ -123,6 +123,7 @@ struct EnvOut {
     int32_t* off_seen;  // (N) all envs: env-local exclusive prefix of the seen degrees
     int32_t* off_near;  // (N)
     int32_t* tot;       // (B, 2): seen / near rows of each env
+    float* state;       // (B, 2U + Fs*G) global state rows, or nullptr
 };
 
 
@@ -454,6 +455,20 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         st.rate[b * G + m] = w.rate[m];
         st.sched[(b * G + m) * 2] = w.sch_ubs[m];
         st.sched[(b * G + m) * 2 + 1] = w.sch_rb[m];
+    }
+    // get_state() (:244-262): [pos_ubs / range_pos | per GT: pos / range_pos, rate / max_rate, avg-rate feature]
+    if (o.state != nullptr) {
+        const int Fs = c.fair_service ? 4 : 3;
+        float* srow = o.state + (size_t)b * (2 * U + Fs * G);
+        for (int i = tid; i < U * 2; i += nthr) srow[i] = (float)(w.pos_u[i] / c.range_pos);
+        for (int m = tid; m < G; m += nthr) {
+            float* g4 = srow + 2 * U + m * Fs;
+            // np: float32 positions (DenseHotSpot, Debug) are divided in float32, float64 positions in float64
+            g4[0] = c.gts_f64 ? (float)((double)w.pos_g[m * 2] / c.range_pos) : w.pos_g[m * 2] / (float)c.range_pos;
+            g4[1] = c.gts_f64 ? (float)((double)w.pos_g[m * 2 + 1] / c.range_pos) : w.pos_g[m * 2 + 1] / (float)c.range_pos;
+            g4[2] = w.f_rate[m];
+            if (c.fair_service) g4[3] = w.f_avg[m];
+        }
     }
     const double ngt = fmin(c.range_pos, c.r_sns), nub = fmin(c.range_pos, c.r_comm);
     for (int p = tid; p < U * G; p += nthr) {

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(const __grid_constant__ S
     o.off_seen = a.scratch + sc.off_off_seen;
     o.off_near = a.scratch + sc.off_off_near;
     o.tot = a.scratch + sc.off_tot;
+    o.state = a.pk.off_state >= 0 ? reinterpret_cast<float*>(a.pk.packet + a.pk.off_state) : nullptr;
     DevCtx ctx{(int)threadIdx.x, (int)blockDim.x, a.profile != 0 && blockIdx.x == 0};
     ctx.mark(0);
     env_run(c, a.st, b, a.actions, a.is_reset != 0, w, o, ctx);

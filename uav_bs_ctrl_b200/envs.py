@@ -27,7 +27,7 @@ INFO_KEYS = ("EpRet", "TotalThroughput", "NColls", "AvgGlobalUtility", "FairIdx"
 class UbsEnvCfg(C.Structure):
     """``ubs_env_cfg`` of ``include/ubs_env.h``."""
     _fields_ = [(n, C.c_int32) for n in ("n_ubs", "n_gts", "n_rbs", "n_actions", "episode_limit", "fair_service",
-                                         "avoid_collision", "reserved")] + \
+                                         "avoid_collision", "gts_f64")] + \
                [(n, C.c_double) for n in ("range_pos", "r_cov", "r_sns", "r_comm", "dt", "rew_scale", "h_ubs", "p_tx",
                                           "n0", "bw", "c_fspl", "chan_a", "chan_b", "k_los", "k_nlos", "max_rate",
                                           "safe_dist", "penalty")] + \
@@ -41,7 +41,7 @@ class UbsEnvState(C.Structure):
 class UbsEnvPacket(C.Structure):
     _fields_ = [("packet", C.c_void_p)] + [(n, C.c_int64) for n in ("off_x_gt", "off_x_ubs", "off_x_agent",
                                                                    "off_ip_seen", "off_ip_near", "off_mask", "off_rew",
-                                                                   "off_done", "off_bad")]
+                                                                   "off_done", "off_bad", "off_state")]
 
 
 # ------------------------------------------------------------------------------------------------------ maps
@@ -195,6 +195,7 @@ def make_cfg(m: Map, fair_service: bool = True, avoid_collision: bool = True) ->
     c = UbsEnvCfg()
     c.n_ubs, c.n_gts, c.n_rbs, c.n_actions = int(m.n_ubs), int(m.n_gts), int(m.n_rbs), int(mv.shape[0])
     c.episode_limit, c.fair_service, c.avoid_collision = int(m.episode_limit), int(fair_service), int(avoid_collision)
+    c.gts_f64 = int(np.asarray(m.set_positions(_pyrandom.Random(0), np.random.RandomState(0))["gt"]).dtype == np.float64)
     c.range_pos, c.r_cov, c.r_sns, c.r_comm = float(m.range_pos), float(m.r_cov), float(m.r_sns), float(m.r_comm)
     c.dt, c.rew_scale = float(m.dt), float(m.reward_scale_rate)
     c.h_ubs, c.p_tx, c.n0, c.bw = H_UBS, float(P_TX), float(N0), BW
@@ -277,6 +278,7 @@ def packet_struct(layout, buf: th.Tensor) -> UbsEnvPacket:
     p.off_x_gt, p.off_x_ubs, p.off_x_agent = o["x_gt"], o["x_ubs"], o["x_agent"]
     p.off_ip_seen, p.off_ip_near, p.off_mask = o["ip_seen"], o["ip_near"], o["mask"]
     p.off_rew, p.off_done, p.off_bad = o["rew"], o["done"], o["bad"]
+    p.off_state = o.get("state", -1)
     return p
 
 
@@ -307,12 +309,18 @@ class MultiUbsCoverageVecEnv:
 
     # reference-shaped metadata (env_wrappers.py:117-120, :62-63)
     def get_env_info(self):
-        return dict(obs_shape=dict(agent=2, ubs=2, gt=4 if self.cfg.fair_service else 3), state_shape=None,
+        return dict(obs_shape=dict(agent=2, ubs=2, gt=4 if self.cfg.fair_service else 3), state_shape=self.state_dim,
                     n_actions=self.n_actions, n_agents=self.n_agents, episode_limit=self.episode_limit)
 
-    def new_layout(self, F_gt=None):
+    @property
+    def state_dim(self) -> int:
+        """``get_state_size()`` (``mubs_cov.py:264-265``)."""
+        return 2 * self.cfg.n_ubs + (4 if self.cfg.fair_service else 3) * self.cfg.n_gts
+
+    def new_layout(self, F_gt=None, with_state=False):
         from .arena import PacketLayout
-        return PacketLayout(self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 2, F_gt or (4 if self.cfg.fair_service else 3), 2)
+        return PacketLayout(self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 2, F_gt or (4 if self.cfg.fair_service else 3), 2,
+                            state_dim=self.state_dim if with_state else 0)
 
     def make_layout_pool(self, n_batches: int, seed0: int = 0):
         """``n_batches`` RNG-matched reset batches sampled ahead of time and parked on the device (the host sampler is

@@ -69,7 +69,7 @@ class ReplayBuffer:
 
 
 class MultiAgentQLearner:
-    """Multi-agent recurrent Q-learner (reference ``algos/madrqn/learner.py:14-201``, no-mixer path)."""
+    """Multi-agent recurrent Q-learner (reference ``algos/madrqn/learner.py:14-201``), optionally with the QMIX mixer."""
 
     def __init__(self, env_info, args):
         self.args = args
@@ -84,9 +84,20 @@ class MultiAgentQLearner:
         self.target_net.load_state_dict(self.policy_net.state_dict())
         self.target_net.eval()
         self.params = list(self.policy_net.parameters())
-        if getattr(args, "mixer", False):
-            raise NotImplementedError("QMixer is outside the hot-path scope (SURVEY §2 row 3)")
         self.mixer = None
+        if getattr(args, "mixer", False):                      # QMIX (reference learner.py:35-40)
+            from .agents.mixers import QMixer
+            if not getattr(args, "share_reward", False):
+                raise ValueError("QMIX mixes the agents' values into one Q_tot: it needs share_reward=True "
+                                 "(reference learner.py:151 expands the rewards to Q_tot's shape)")
+            if not self.state_shape:
+                raise ValueError("QMIX needs the global state size in env_info['state_shape']")
+            if not hasattr(args, "embed_dim"):
+                args.embed_dim = 32                           # reference config.py:19
+            self.mixer = QMixer(self.state_shape, self.n_agents, args).to(self.device)
+            dist.sync_params(self.mixer)
+            self.target_mixer = deepcopy(self.mixer).to(self.device)
+            self.params += list(self.mixer.parameters())
 
         self.max_seq_len = args.max_seq_len if args.max_seq_len is not None else env_info["episode_limit"]
         self.gamma, self.polyak, self.batch_size = args.gamma, args.polyak, args.batch_size
@@ -166,12 +177,13 @@ class MultiAgentQLearner:
         agent_out.append(logits)
         return th.stack(agent_out), th.stack(target_out)
 
-    def compute_loss(self, obs, h, h_targ, acts, rews, dones):
+    def compute_loss(self, obs, h, h_targ, acts, rews, dones, states=None):
         agent_out, target_out = self._unroll(obs, h, h_targ)
-        return self._td_loss(agent_out, target_out, acts, rews, dones)
+        return self._td_loss(agent_out, target_out, acts, rews, dones, states)
 
-    def _td_loss(self, agent_out, target_out, acts, rews, dones):
-        """Reference ``learner.py:134-154`` (no mixer): ``agent_out (T+1,N,A)``, ``target_out (T,N,A)``."""
+    def _td_loss(self, agent_out, target_out, acts, rews, dones, states=None):
+        """Reference ``learner.py:134-154``: ``agent_out (T+1,N,A)``, ``target_out (T,N,A)``; with the mixer,
+        ``states (T+1, n_seq, S)`` turn the per-agent values into ``Q_tot`` (``:144-148``)."""
         T = target_out.shape[0]
         qvals = agent_out[:-1].gather(2, acts)
         if not self.double_q:
@@ -182,6 +194,12 @@ class MultiAgentQLearner:
         n_seq = rews.shape[1]
         qvals = qvals.view(T, n_seq, self.n_agents)
         next_vals = next_vals.view(T, n_seq, self.n_agents)
+        if self.mixer is not None:
+            if states is None:
+                raise ValueError("QMIX update without global states")
+            qvals = self.mixer(qvals, states[:-1])
+            with th.no_grad():
+                next_vals = self.target_mixer(next_vals, states[1:])
         rews, dones = rews.expand_as(next_vals), dones.expand_as(next_vals)
         target_qvals = rews + self.gamma * (1 - dones) * next_vals
         return self.loss_fn(qvals, target_qvals), qvals
@@ -203,6 +221,7 @@ class MultiAgentQLearner:
         dones = th.stack(batch["done"]).to(dev)
         h, h_targ = batch["h"][0].to(dev), batch["h"][1].to(dev)
         obs = [o.to(dev) for o in batch["obs"]]
+        self._batch_states = th.stack(batch["state"]).to(dev) if batch.get("state") else None   # (T+1, n_seq·n_envs, S)
         return obs, h, h_targ, acts, rews, dones
 
     def update(self, samples=None, sync=True):
@@ -211,7 +230,7 @@ class MultiAgentQLearner:
             assert len(self.buffer) >= self.batch_size, "Insufficient samples for update."
             samples = self.buffer.sample(self.batch_size)
         obs, h, h_targ, acts, rews, dones = self.gather_batch(samples)
-        loss, qvals = self.compute_loss(obs, h, h_targ, acts, rews, dones)
+        loss, qvals = self.compute_loss(obs, h, h_targ, acts, rews, dones, self._batch_states)
         return self._optimise(loss, qvals, sync)
 
     def _optimise(self, loss, qvals, sync):
@@ -224,6 +243,8 @@ class MultiAgentQLearner:
         self.optimizer.step()
         with th.no_grad():
             pp, tp = list(self.policy_net.parameters()), list(self.target_net.parameters())
+            if self.mixer is not None:                                       # reference learner.py:168-171
+                pp, tp = pp + list(self.mixer.parameters()), tp + list(self.target_mixer.parameters())
             th._foreach_mul_(tp, self.polyak)
             th._foreach_add_(tp, pp, alpha=1 - self.polyak)
         if sync:
@@ -236,7 +257,7 @@ class MultiAgentQLearner:
         from .arena import PacketLayout, SequenceArena
         fg = self.obs_shape["gt"] if isinstance(self.obs_shape, dict) else 4
         L = PacketLayout(self.n_envs, self.n_agents, n_gts, F_ag=self.obs_shape["agent"], F_gt=fg,
-                         F_ubs=self.obs_shape["ubs"])
+                         F_ubs=self.obs_shape["ubs"], state_dim=int(self.state_shape or 0) if self.mixer is not None else 0)
         return SequenceArena(L, n_slots or self.max_seq_len + 1, self.args.hidden_size, self.device)
 
     def begin_sequence(self, arena, h0=None):
@@ -351,7 +372,8 @@ class MultiAgentQLearner:
         agent_out, _ = self.policy_net.arena_sequence(arena, 0, T + 1, h0)
         with th.no_grad():
             target_out, _ = self.target_net.arena_sequence(arena, 1, T, h_targ)
-        loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones)
+        states = arena.states(T + 1) if self.mixer is not None else None
+        loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones, states)
         out = self._optimise(loss, qvals, sync)
         # refresh the packed weights outside any captured graph (AdamW / polyak updated the parameters in place)
         for net in (self.policy_net, self.target_net):
@@ -363,6 +385,8 @@ class MultiAgentQLearner:
         checkpoint = dict(stamp)
         checkpoint["model_state_dict"] = self.policy_net.state_dict()
         checkpoint["optimizer_state_dict"] = self.optimizer.state_dict()
+        if self.mixer is not None:
+            checkpoint["mixer_state_dict"] = self.mixer.state_dict()
         if self.anneal_lr:
             checkpoint["lr_scheduler_state_dict"] = self.lr_scheduler.state_dict()
         th.save(checkpoint, path)
@@ -373,6 +397,9 @@ class MultiAgentQLearner:
         self.policy_net.load_state_dict(checkpoint["model_state_dict"])
         self.target_net.load_state_dict(self.policy_net.state_dict())
         self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        if self.mixer is not None:
+            self.mixer.load_state_dict(checkpoint["mixer_state_dict"])
+            self.target_mixer.load_state_dict(self.mixer.state_dict())
         if self.anneal_lr:
             self.lr_scheduler.load_state_dict(checkpoint["lr_scheduler_state_dict"])
         return stamp

@@ -68,6 +68,10 @@ typedef struct {
     int32_t* packet;
     int64_t off_x_gt, off_x_ubs, off_x_agent, off_ip_seen, off_ip_near, off_mask, off_rew, off_done, off_bad;
     int64_t off_state; /* (B, 2U + (3 + fair_service) G) global state of get_state() (mubs_cov.py:244-262) for QMIX; -1: not stored */
+    int64_t off_flat;  /* (B*U, ld_flat) flattened local observations for the MLP encoder (FlattenedObservation,
+                          env_wrappers.py:41-54: gym flattens the Dict in key order agent | gt | ubs, flags included);
+                          -1: not stored */
+    int64_t ld_flat;   /* row pitch in floats, >= 2 + G (2 + 3 + fair_service) ... see envs.flat_obs_dim(); the pad is zero */
 } ubs_env_packet;
 
 /* Words of device scratch ubs_env_step / ubs_env_reset need for B envs (staging of the per-env compacted rows). */

@@ -61,8 +61,9 @@ class HostEnv:
         self.lib, self.cfg, self.B = _host_lib(), cfg, B
         self.buf = E.EnvBuffers(cfg, B, "cpu", self.lib.ubs_env_host_scratch_words(C.byref(cfg), B))
         fg = 4 if cfg.fair_service else 3
-        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts)
-        self.packet = th.zeros(self.layout.words, dtype=th.int32)
+        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts,
+                                   flat_dim=E.flat_obs_dim(cfg))
+        self.packet = th.full((self.layout.words,), 0x7fc00000, dtype=th.int32)      # NaN-filled: every word must be written
 
     def run(self, actions=None):
         st, pk = self.buf.state_struct(), E.packet_struct(self.layout, self.packet)
@@ -81,8 +82,9 @@ class DevEnv:
         self._lib, self.lib, self.cfg, self.B = _lib, _lib.load(), cfg, B
         self.buf = E.EnvBuffers(cfg, B, "cuda", self.lib.ubs_env_scratch_words(C.byref(cfg), B))
         fg = 4 if cfg.fair_service else 3
-        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts)
-        self.packet = th.zeros(self.layout.words, dtype=th.int32, device="cuda")
+        self.layout = PacketLayout(B, cfg.n_ubs, cfg.n_gts, 2, fg, 2, state_dim=2 * cfg.n_ubs + fg * cfg.n_gts,
+                                   flat_dim=E.flat_obs_dim(cfg))
+        self.packet = th.full((self.layout.words,), 0x7fc00000, dtype=th.int32, device="cuda")
 
     def run(self, actions=None):
         st, pk = self.buf.state_struct(), E.packet_struct(self.layout, self.packet)
@@ -178,6 +180,12 @@ def check_snapshot(env, e, k, b=0, check_prior=True):
         ref_mask[d] |= 1 << int(s)
     assert np.array_equal(mask, ref_mask), f"step {k}: talk mask"
     close(L.section(pkt, "rew").numpy()[b * U:(b + 1) * U], e["reward"][k], f"step {k}: reward", scale=1.0)
+    # flattened local observations (FlattenedObservation: agent | gt rows | ubs rows, flags included), zero row pad
+    flat = L.section(pkt, "x_flat").numpy().reshape(-1, L.flat_ld)[b * U:(b + 1) * U]
+    ref_flat = np.concatenate([e["obs_agent"][k].reshape(U, -1), e["obs_gt"][k].reshape(U, -1), e["obs_ubs"][k].reshape(U, -1)], 1)
+    assert ref_flat.shape[1] == L.flat_dim
+    close(flat[:, :L.flat_dim], ref_flat, f"step {k}: flattened observations", scale=1.0)
+    assert not flat[:, L.flat_dim:].any(), f"step {k}: pad columns of the flattened observations must be zero"
     sd = L.state_dim                                          # get_state() -> the QMIX mixer's input
     close(L.section(pkt, "state").numpy()[b * sd:(b + 1) * sd], e["state"][k], f"step {k}: global state", scale=1.0)
     assert float(L.section(pkt, "done")[b]) == float(e["done"][k]) and float(L.section(pkt, "bad")[b]) == float(e["bad"][k])
@@ -358,5 +366,43 @@ def test_full_loop_act_env_update_on_the_arena():
     assert th.equal(env.buf.t.cpu(), th.full((B,), T, dtype=th.int32))
     g = arena.graph(T)
     assert g.num_nodes("agent") == B * 8 and g["near"].num_edges() == B * 8 * 7 and g["talk"].num_edges() == B * 64
+    out = learner.update_arena(arena, sync=True)
+    assert np.isfinite(out["LossQ"])
+
+
+@pytest.mark.gpu
+def test_full_loop_with_the_mlp_encoder_on_flattened_observations():
+    """exp2-style agent (o='mlp': DenseObservationEncoder over the flattened observation + TarMAC) on the device env:
+    the arena path equals the module called on graphs built from the same packets, and an update runs."""
+    from types import SimpleNamespace
+    from uav_bs_ctrl_b200.learner import MultiAgentQLearner
+    B, T = 8, 4
+    env = E.MultiUbsCoverageVecEnv("r400", B)                       # HotSpot 4 UBS x 4 GT, finite r_comm (exp2 maps)
+    info = env.get_env_info(o="mlp")
+    info["episode_limit"] = T
+    assert info["obs_shape"] == 2 + 4 * 5 + 3 * 3
+    args = SimpleNamespace(device="cuda", o="mlp", c="tarmac", share_reward=False, hidden_size=64, n_layers=2, n_heads=4,
+                           msg_size=64, key_size=16, n_rounds=1, lr=2.5e-4, gamma=0.99, polyak=0.999, batch_size=1,
+                           replay_size=2, max_seq_len=T, anneal_lr=False, double_q=True, dueling=False, mixer=False,
+                           n_envs=B, cuda_graphs=True)
+    th.manual_seed(0)
+    learner = MultiAgentQLearner(info, args)
+    arena = learner.new_arena(env.cfg.n_gts)
+    assert arena.layout.flat_dim == info["obs_shape"]
+    learner.begin_sequence(arena)
+    env.reset(arena, 0, seeds=range(B))
+    learner.rollout_arena(env, arena, 0.2)
+    th.cuda.synchronize()
+    # the fused arena step vs the plain module on (comm graph, flat features) of the same slot
+    net = learner.policy_net
+    with th.no_grad():
+        for t in (0, T - 1):
+            g = arena.graph(t)
+            g.nodes["agent"].data["feat"] = arena.flat_obs(t, 1)[0].contiguous()
+            q_ref, h_ref = net(g, arena.h[t])
+            assert th.allclose(h_ref, arena.h[t + 1], rtol=2e-5, atol=2e-6)
+            greedy = q_ref.argmax(1)
+            explored = arena.explore_u[t] <= 0.2
+            assert th.equal(arena.acts[t][~explored], greedy[~explored])
     out = learner.update_arena(arena, sync=True)
     assert np.isfinite(out["LossQ"])

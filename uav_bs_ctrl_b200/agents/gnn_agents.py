@@ -439,16 +439,23 @@ class GnnAgent(nn.Module):
         return out.view(T, L.N, 2 * self._hidden_size)
 
     def arena_dims(self, arena):
-        if not isinstance(self.enc, GraphObservationEncoder):
+        if not isinstance(self.enc, GraphObservationEncoder) and not arena.layout.flat_dim:
             return None
         return self.fused_dims(arena.layout.U)
+
+    def _arena_flat_x(self, arena, t0, T):
+        """MLP encoder (``DenseObservationEncoder``, reference ``gnn_agents.py:62-77``) over the flattened observations
+        of arena slots ``t0 .. t0+T-1`` -> ``(T, N, H)``: plain library GEMMs (with autograd when enabled) reading
+        the packets in place."""
+        return self.enc.enc(arena.flat_obs(t0, T))
 
     def arena_sequence(self, arena, t0, T, h0):
         """``forward_sequence`` over arena slots ``t0 .. t0+T-1`` (with autograd when enabled)."""
         dims = self.arena_dims(arena)
         if dims is None:
-            raise NotImplementedError("arena path needs the graph encoder and the fused step configuration")
-        xin = self._arena_xin(arena, t0, T)
+            raise NotImplementedError("arena path needs the fused step configuration (and, for the MLP encoder, an arena "
+                                      "with flattened observations)")
+        xin = self._arena_xin(arena, t0, T) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t0, T)
         mask = arena.sec("mask")[t0:t0 + T].contiguous() if dims.tarmac else None
         return self._run_sequence(dims, xin, h0.contiguous(), mask)
 
@@ -458,7 +465,7 @@ class GnnAgent(nn.Module):
         returns the Q values.  Three launches (two relations + the fused step), no allocation-dependent host logic,
         so the call can be captured in a CUDA graph."""
         dims = self.arena_dims(arena)
-        xin = self._arena_xin(arena, t, 1)
+        xin = self._arena_xin(arena, t, 1) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t, 1)
         mask = arena.sec("mask", t) if dims.tarmac else None
         if self.use_seq2_act and self.use_seq2 and ops.seq2_supported(dims):
             # two small library GEMMs (aggregator; fused [pv | pg]) + the resident-weight kernel with T = 1 + Q head

@@ -33,9 +33,10 @@ def _al4(n: int) -> int:
 class PacketLayout:
     """Word offsets of the sections of one observation packet for ``B`` envs × ``U`` agents × ``G`` ground terminals."""
 
-    FLOAT = ("x_gt", "x_ubs", "x_agent", "rew", "done", "bad", "state")
+    FLOAT = ("x_gt", "x_ubs", "x_agent", "rew", "done", "bad", "state", "x_flat")
 
-    def __init__(self, B: int, U: int, G: int, F_ag: int = 2, F_gt: int = 4, F_ubs: int = 2, state_dim: int = 0):
+    def __init__(self, B: int, U: int, G: int, F_ag: int = 2, F_gt: int = 4, F_ubs: int = 2, state_dim: int = 0,
+                 flat_dim: int = 0):
         self.B, self.U, self.G, self.N = B, U, G, B * U
         self.F_ag, self.F_gt, self.F_ubs = F_ag, F_gt, F_ubs
         N = self.N
@@ -45,6 +46,11 @@ class PacketLayout:
         self.state_dim = state_dim                                   # global env state (QMIX), optional last section
         if state_dim:
             sizes.append(("state", B * state_dim))
+        # flattened local observations for the MLP encoder (optional): rows padded to a multiple of 32 floats so that
+        # the first encoder layer can run on the tcgen05 projection kernel (K % 32 == 0); the pad columns are zero
+        self.flat_dim, self.flat_ld = flat_dim, (flat_dim + 31) // 32 * 32
+        if flat_dim:
+            sizes.append(("x_flat", N * self.flat_ld))
         self.off: Dict[str, int] = {}
         self.size: Dict[str, int] = {}
         o = 0
@@ -59,7 +65,7 @@ class PacketLayout:
         return v.view(th.float32) if name in self.FLOAT else v
 
     def key(self):
-        return (self.B, self.U, self.G, self.F_ag, self.F_gt, self.F_ubs, self.state_dim)
+        return (self.B, self.U, self.G, self.F_ag, self.F_gt, self.F_ubs, self.state_dim, self.flat_dim)
 
 
 class ObsPacket:
@@ -175,6 +181,13 @@ class SequenceArena:
     def rewards(self, T: int) -> th.Tensor:
         """``(T, B, U)`` rewards of transitions 0..T-1 (stored with observations 1..T)."""
         return self.sec("rew")[1:T + 1].reshape(T, self.layout.B, self.layout.U)
+
+    def flat_obs(self, t0: int, T: int) -> th.Tensor:
+        """``(T, N, flat_dim)`` flattened local observations of slots ``t0 .. t0+T-1`` (a strided view, pad cut off)."""
+        L = self.layout
+        if not L.flat_dim:
+            raise ValueError("this arena was created without flattened observations (PacketLayout(flat_dim=...))")
+        return self.sec("x_flat")[t0:t0 + T].view(T, L.N, L.flat_ld)[..., :L.flat_dim]
 
     def states(self, T: int) -> th.Tensor:
         """``(T, B, state_dim)`` global states of slots 0..T-1 (QMIX)."""

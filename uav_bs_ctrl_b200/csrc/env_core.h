@@ -124,6 +124,8 @@ struct EnvOut {
     int32_t* off_near;  // (N)
     int32_t* tot;       // (B, 2): seen / near rows of each env
     float* state;       // (B, 2U + Fs*G) global state rows, or nullptr
+    float* flat;        // (N, ld_flat) flattened local observations [agent | gt rows with flag | ubs rows with flag], or nullptr
+    int64_t ld_flat;
 };
 
 
@@ -471,23 +473,49 @@ UBS_HD inline void env_run(const ubs_env_cfg& c, const ubs_env_state& st, int64_
         }
     }
     const double ngt = fmin(c.range_pos, c.r_sns), nub = fmin(c.range_pos, c.r_comm);
+    // flattened observation rows keep every GT / UBS slot (zeros when not visible) with its flag (:225-240)
+    const int flat_gt0 = 2, flat_ubs0 = 2 + G * (1 + Fg), flat_dim = flat_ubs0 + (U - 1) * 3;
     for (int p = tid; p < U * G; p += nthr) {
         const int s = w.slot[p];
-        if (s < 0) continue;
         const int i = p / G, m = p - i * G;
-        float* row = o.stage_gt + (size_t)(w.deg[2 * U + i] + s) * Fg;
-        row[0] = (float)(((double)w.pos_g[m * 2] - w.pos_u[i * 2]) / ngt);       // np: float32 - float64 -> float64
-        row[1] = (float)(((double)w.pos_g[m * 2 + 1] - w.pos_u[i * 2 + 1]) / ngt);
-        row[2] = w.f_rate[m];
-        if (c.fair_service) row[3] = w.f_avg[m];
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        if (s >= 0) {
+            r0 = (float)(((double)w.pos_g[m * 2] - w.pos_u[i * 2]) / ngt);       // np: float32 - float64 -> float64
+            r1 = (float)(((double)w.pos_g[m * 2 + 1] - w.pos_u[i * 2 + 1]) / ngt);
+            r2 = w.f_rate[m];
+            r3 = w.f_avg[m];
+            float* row = o.stage_gt + (size_t)(w.deg[2 * U + i] + s) * Fg;
+            row[0] = r0; row[1] = r1; row[2] = r2;
+            if (c.fair_service) row[3] = r3;
+        }
+        if (o.flat != nullptr) {
+            float* fr = o.flat + (size_t)(b * U + i) * o.ld_flat + flat_gt0 + m * (1 + Fg);
+            fr[0] = s >= 0 ? 1.f : 0.f;
+            fr[1] = r0; fr[2] = r1; fr[3] = r2;
+            if (c.fair_service) fr[4] = r3;
+        }
     }
     for (int p = tid; p < U * U; p += nthr) {
         const int s = w.nslot[p];
-        if (s < 0) continue;
         const int i = p / U, j = p - i * U;
-        float* row = o.stage_ubs + (size_t)(w.deg[3 * U + i] + s) * 2;
-        row[0] = (float)((w.pos_u[j * 2] - w.pos_u[i * 2]) / nub);
-        row[1] = (float)((w.pos_u[j * 2 + 1] - w.pos_u[i * 2 + 1]) / nub);
+        float r0 = 0.f, r1 = 0.f;
+        if (s >= 0) {
+            r0 = (float)((w.pos_u[j * 2] - w.pos_u[i * 2]) / nub);
+            r1 = (float)((w.pos_u[j * 2 + 1] - w.pos_u[i * 2 + 1]) / nub);
+            float* row = o.stage_ubs + (size_t)(w.deg[3 * U + i] + s) * 2;
+            row[0] = r0; row[1] = r1;
+        }
+        if (o.flat != nullptr && j != i) {
+            float* fr = o.flat + (size_t)(b * U + i) * o.ld_flat + flat_ubs0 + (j < i ? j : j - 1) * 3;
+            fr[0] = s >= 0 ? 1.f : 0.f;
+            fr[1] = r0; fr[2] = r1;
+        }
+    }
+    if (o.flat != nullptr) {
+        for (int p = tid; p < U * 2; p += nthr)                                   // own features (:223)
+            o.flat[(size_t)(b * U + p / 2) * o.ld_flat + (p & 1)] = (float)(w.pos_u[p] / c.range_pos);
+        const int pad = (int)o.ld_flat - flat_dim;
+        for (int p = tid; p < U * pad; p += nthr) o.flat[(size_t)(b * U + p / pad) * o.ld_flat + flat_dim + p % pad] = 0.f;
     }
 }
 

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(256) env_step_kernel(const __grid_constant__ S
     o.off_near = a.scratch + sc.off_off_near;
     o.tot = a.scratch + sc.off_tot;
     o.state = a.pk.off_state >= 0 ? reinterpret_cast<float*>(a.pk.packet + a.pk.off_state) : nullptr;
+    o.flat = a.pk.off_flat >= 0 ? reinterpret_cast<float*>(a.pk.packet + a.pk.off_flat) : nullptr;
+    o.ld_flat = a.pk.ld_flat;
     DevCtx ctx{(int)threadIdx.x, (int)blockDim.x, a.profile != 0 && blockIdx.x == 0};
     ctx.mark(0);
     env_run(c, a.st, b, a.actions, a.is_reset != 0, w, o, ctx);
@@ -119,6 +121,8 @@ static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* s
     UBS_REQUIRE(st->pos_ubs && st->pos_gts && st->avg_rate && st->rate && st->prior && st->t && st->info && st->sched,
                 "%s: NULL state pointer", fn);
     UBS_REQUIRE(pk->packet != nullptr, "%s: NULL packet", fn);
+    UBS_REQUIRE(pk->off_flat < 0 || pk->ld_flat >= 2 + cfg->n_gts * (cfg->fair_service ? 5 : 4) + (cfg->n_ubs - 1) * 3,
+                "%s: ld_flat smaller than the flattened observation", fn);
     UBS_REQUIRE(is_reset || actions != nullptr, "%s: NULL actions", fn);
     UBS_REQUIRE(B >= 0 && B * cfg->n_ubs < (1ll << 31) / (cfg->n_gts > 0 ? cfg->n_gts : 1), "%s: batch out of range", fn);
     if (B == 0) return 0;

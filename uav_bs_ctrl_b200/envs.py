@@ -41,7 +41,8 @@ class UbsEnvState(C.Structure):
 class UbsEnvPacket(C.Structure):
     _fields_ = [("packet", C.c_void_p)] + [(n, C.c_int64) for n in ("off_x_gt", "off_x_ubs", "off_x_agent",
                                                                    "off_ip_seen", "off_ip_near", "off_mask", "off_rew",
-                                                                   "off_done", "off_bad", "off_state")]
+                                                                   "off_done", "off_bad", "off_state", "off_flat",
+                                                                   "ld_flat")]
 
 
 # ------------------------------------------------------------------------------------------------------ maps
@@ -209,6 +210,11 @@ def make_cfg(m: Map, fair_service: bool = True, avoid_collision: bool = True) ->
     return c
 
 
+def flat_obs_dim(cfg: UbsEnvCfg) -> int:
+    """2 own features + G rows of (flag, dx, dy, rate[, avg rate]) + (U-1) rows of (flag, dx, dy)  (``mubs_cov.py:247-278``)."""
+    return 2 + cfg.n_gts * (5 if cfg.fair_service else 4) + (cfg.n_ubs - 1) * 3
+
+
 def sample_layouts(m: Map, seeds: Sequence[int]):
     """RNG-matched ``reset`` draws for ``len(seeds)`` env instances: what the reference produces after
     ``random.seed(s); np.random.seed(s)`` — ``map.set_positions()`` then ``np.random.permutation(n_gts)``
@@ -279,6 +285,7 @@ def packet_struct(layout, buf: th.Tensor) -> UbsEnvPacket:
     p.off_ip_seen, p.off_ip_near, p.off_mask = o["ip_seen"], o["ip_near"], o["mask"]
     p.off_rew, p.off_done, p.off_bad = o["rew"], o["done"], o["bad"]
     p.off_state = o.get("state", -1)
+    p.off_flat, p.ld_flat = o.get("x_flat", -1), layout.flat_ld
     return p
 
 
@@ -308,7 +315,11 @@ class MultiUbsCoverageVecEnv:
         self._episode = 0
 
     # reference-shaped metadata (env_wrappers.py:117-120, :62-63)
-    def get_env_info(self):
+    def get_env_info(self, o="gnn"):
+        """``o='gnn'``: graph observations (``GraphObservation.get_obs_size``); ``o='mlp'``: flattened observations."""
+        if o == "mlp":
+            return dict(obs_shape=self.flat_obs_dim, state_shape=self.state_dim, n_actions=self.n_actions,
+                        n_agents=self.n_agents, episode_limit=self.episode_limit)
         return dict(obs_shape=dict(agent=2, ubs=2, gt=4 if self.cfg.fair_service else 3), state_shape=self.state_dim,
                     n_actions=self.n_actions, n_agents=self.n_agents, episode_limit=self.episode_limit)
 
@@ -317,10 +328,15 @@ class MultiUbsCoverageVecEnv:
         """``get_state_size()`` (``mubs_cov.py:264-265``)."""
         return 2 * self.cfg.n_ubs + (4 if self.cfg.fair_service else 3) * self.cfg.n_gts
 
-    def new_layout(self, F_gt=None, with_state=False):
+    @property
+    def flat_obs_dim(self) -> int:
+        """Size of a flattened local observation (``FlattenedObservation.get_obs_size``, ``env_wrappers.py:48-49``)."""
+        return flat_obs_dim(self.cfg)
+
+    def new_layout(self, F_gt=None, with_state=False, with_flat=False):
         from .arena import PacketLayout
         return PacketLayout(self.n_envs, self.cfg.n_ubs, self.cfg.n_gts, 2, F_gt or (4 if self.cfg.fair_service else 3), 2,
-                            state_dim=self.state_dim if with_state else 0)
+                            state_dim=self.state_dim if with_state else 0, flat_dim=self.flat_obs_dim if with_flat else 0)
 
     def make_layout_pool(self, n_batches: int, seed0: int = 0):
         """``n_batches`` RNG-matched reset batches sampled ahead of time and parked on the device (the host sampler is

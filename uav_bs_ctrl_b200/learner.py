@@ -255,9 +255,12 @@ class MultiAgentQLearner:
     def new_arena(self, n_gts, n_slots=None):
         """Device-resident replay entry: ``max_seq_len + 1`` observation packets + hidden states + actions."""
         from .arena import PacketLayout, SequenceArena
-        fg = self.obs_shape["gt"] if isinstance(self.obs_shape, dict) else 4
-        L = PacketLayout(self.n_envs, self.n_agents, n_gts, F_ag=self.obs_shape["agent"], F_gt=fg,
-                         F_ubs=self.obs_shape["ubs"], state_dim=int(self.state_shape or 0) if self.mixer is not None else 0)
+        graph_obs = isinstance(self.obs_shape, dict)
+        fg = self.obs_shape["gt"] if graph_obs else getattr(self.args, "F_gt", 4)
+        L = PacketLayout(self.n_envs, self.n_agents, n_gts, F_ag=self.obs_shape["agent"] if graph_obs else 2, F_gt=fg,
+                         F_ubs=self.obs_shape["ubs"] if graph_obs else 2,
+                         state_dim=int(self.state_shape or 0) if self.mixer is not None else 0,
+                         flat_dim=0 if graph_obs else int(self.obs_shape))
         return SequenceArena(L, n_slots or self.max_seq_len + 1, self.args.hidden_size, self.device)
 
     def begin_sequence(self, arena, h0=None):

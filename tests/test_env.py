@@ -406,3 +406,33 @@ def test_full_loop_with_the_mlp_encoder_on_flattened_observations():
             assert th.equal(arena.acts[t][~explored], greedy[~explored])
     out = learner.update_arena(arena, sync=True)
     assert np.isfinite(out["LossQ"])
+
+
+@pytest.mark.gpu
+def test_full_loop_on_the_scaled_config():
+    """BASELINE 'exp3 scaled': 16 UBS x 320 GT, hidden 128 (streamed-weight kernels, 125 KB env working set)."""
+    from types import SimpleNamespace
+    from uav_bs_ctrl_b200.learner import MultiAgentQLearner
+    B, T = 4, 3
+    env = E.MultiUbsCoverageVecEnv("16ubs320", B)
+    info = env.get_env_info()
+    info["episode_limit"] = T
+    args = SimpleNamespace(device="cuda", o="gnn", c="tarmac", share_reward=False, hidden_size=128, n_layers=2, n_heads=4,
+                           msg_size=64, key_size=16, n_rounds=1, lr=2.5e-4, gamma=0.99, polyak=0.999, batch_size=1,
+                           replay_size=2, max_seq_len=T, anneal_lr=False, double_q=True, dueling=False, mixer=False,
+                           n_envs=B, cuda_graphs=True)
+    th.manual_seed(0)
+    learner = MultiAgentQLearner(info, args)
+    arena = learner.new_arena(env.cfg.n_gts)
+    m = env.map
+    pu, pg, pr = E.sample_layouts(m, range(B))
+    pu[:2] = pg[:2, :m.n_ubs].astype(np.float64) + 20.0               # two instances start inside the hot spot
+    for cycle in range(2):
+        learner.begin_sequence(arena)
+        env.reset(arena, 0, layouts=(pu, pg, pr))
+        learner.rollout_arena(env, arena, 0.3)
+        out = learner.update_arena(arena, sync=True)
+        assert np.isfinite(out["LossQ"])
+    assert int(arena.sec("ip_seen")[T, -1]) > 100 and int((env.buf.sched[..., 0] >= 0).sum()) > 0
+    g = arena.graph(T)
+    assert g.num_nodes("agent") == B * 16 and g["talk"].num_edges() == B * 256

@@ -12,7 +12,15 @@ GPU, every GT visible (full degree: E_seen = N·G, the heaviest degree profile),
     python bench.py --gpus N --steps K --warmup W                  # this framework
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle (DGL-equivalent restatement)
 
-Prints ONE JSON line (rank 0).  See DESIGN.md §d for every field.
+Prints ONE JSON line (rank 0).  Legs of that line:
+  value      observations resident in the sequence arena; the T act steps of a window are ONE CUDA graph
+             (`--per-step-graphs`: one replay per vector-step), then `update_arena`
+  e2e        the same cycle fed from pinned HOST packets: one H2D copy + actions D2H + stream sync per vector-step
+  full_loop  the device-resident MultiUbsCoverageEnv (ubs_env_step) produces every observation: reset, ONE graph
+             with T x (relations + act + env step + pack), update — nothing returns to the host inside a cycle
+  roofline   dominant (kernel, shape) group of one extra eager cycle, CUDA events around each C-ABI call; `groups`
+             lists every kernel group with its algorithmic GB/s and FP32 TFLOP/s
+  cpu_baseline / --impl reference   the DGL-equivalent CPU oracle on the box's host cores (bounded sample)
 """
 from __future__ import annotations
 

@@ -436,3 +436,26 @@ def test_full_loop_on_the_scaled_config():
     assert int(arena.sec("ip_seen")[T, -1]) > 100 and int((env.buf.sched[..., 0] >= 0).sum()) > 0
     g = arena.graph(T)
     assert g.num_nodes("agent") == B * 16 and g["talk"].num_edges() == B * 256
+
+
+def test_snapshot_restore_resumes_an_episode_identically():
+    """Checkpoint / resume of the env state (EnvBuffers.snapshot / restore): the continuation after a restore is
+    bit-identical to the uninterrupted episode."""
+    e = ep("8ubs_stable_hover")
+    _, cfg = cfg_for("8ubs_stable_hover")
+    env = HostEnv(cfg)
+    load_state(env, e, 0, prior=e["prior_in0"])
+    env.run(None)
+    for k in range(1, 11):
+        env.run(e["actions"][k])
+    snap = env.buf.snapshot()
+    tail = []
+    for k in range(11, 21):
+        tail.append(env.run(e["actions"][k]).clone())
+    env.buf.restore(snap)
+    for i, k in enumerate(range(11, 21)):
+        pkt = env.run(e["actions"][k])
+        L = env.layout
+        for sec in ("x_agent", "ip_seen", "ip_near", "mask", "rew", "done", "state", "x_flat"):
+            assert th.equal(L.section(pkt, sec), L.section(tail[i], sec)), (k, sec)
+    check_snapshot(env, e, 20)

@@ -270,8 +270,85 @@ class CommNet(nn.Module):
         return h
 
 
+def gumbel_softmax_hard(logits, gumbels, tau):
+    """``F.gumbel_softmax(logits, tau, hard=True)`` of PyTorch with the noise made explicit
+    (``gumbels = -log(Exponential(1))``): straight-through one-hot, ``y_hard - y_soft.detach() + y_soft``."""
+    y_soft = ((logits + gumbels) / tau).softmax(-1)
+    index = y_soft.max(-1, keepdim=True)[1]
+    y_hard = th.zeros_like(logits).scatter_(-1, index, 1.0)
+    return y_hard - y_soft.detach() + y_soft
+
+
+def _segment_max(dst, m, n):
+    """UDF reduce ``nodes.mailbox['m'].max(1)[0]`` (``gnn_agents.py:176-179``): mailbox rows in edge-id order, the
+    gradient follows ``torch.max(dim)`` (ONE winner per (node, feature)); nodes without messages get zeros."""
+    deg = th.bincount(dst, minlength=n)
+    dmax = int(deg.max()) if dst.numel() else 0
+    if dmax == 0:
+        return th.zeros((n,) + tuple(m.shape[1:]), dtype=m.dtype)
+    order = th.sort(dst, stable=True)[1]
+    start = th.cumsum(deg, 0) - deg
+    slot = th.arange(dst.numel()) - start[dst[order]]
+    box = th.full((n, dmax) + tuple(m.shape[1:]), float("-inf"), dtype=m.dtype)
+    box = box.index_put((dst[order], slot), m[order])
+    out = box.max(1)[0]
+    return th.where((deg > 0).view((-1,) + (1,) * (m.dim() - 1)), out, th.zeros_like(out))
+
+
+class DiscreteComm(nn.Module):
+    """Reference ``gnn_agents.py:151-193``: per-EDGE hard Gumbel-softmax bits of ``f_enc([x_u ‖ h_u.detach()])``
+    (tau = 0.5), element-wise max over in-edges, ``f_dec``, GRU.  ``exponential_feed``: optional iterator of the
+    ``Exponential(1)`` draws (E, msg, 2) in edge-id order, one per call (else drawn from the torch RNG)."""
+
+    def __init__(self, args):
+        super().__init__()
+        H, M = args.hidden_size, args.msg_size
+        self._hidden_size, self._msg_size = H, M
+        self.f_enc = nn.Linear(2 * H, 2 * M)
+        self.f_dec = nn.Linear(2 * M, 2 * M)
+        self.f_udt = nn.GRUCell(H + 2 * M, H)
+        self.exponential_feed = None
+
+    def forward(self, g, x, h):
+        src, dst = g.edges()
+        if g.number_of_edges() == 0:
+            c = th.zeros(x.shape[0], 2 * self._msg_size, dtype=x.dtype)
+        else:
+            logits = self.f_enc(th.cat((x, h.detach()), 1).index_select(0, src)).view(-1, self._msg_size, 2)
+            if self.exponential_feed is not None:
+                e = next(self.exponential_feed).to(logits.dtype)
+            else:
+                e = th.empty_like(logits).exponential_()
+            m = gumbel_softmax_hard(logits, -e.log(), 0.5).flatten(1)
+            c = _segment_max(dst, m, x.shape[0])
+        return self.f_udt(th.cat((x, self.f_dec(c)), 1), h)
+
+
+class EdgeConv(nn.Module):
+    """Reference ``gnn_agents.py:274-299``: message ``f_msg([x_u ‖ h_u ‖ x_v ‖ h_v])`` (h detached), mean, GRU."""
+
+    def __init__(self, args):
+        super().__init__()
+        H, M = args.hidden_size, args.msg_size
+        self._hidden_size, self._n_rounds = H, args.n_rounds
+        self.f_msg = nn.Linear(4 * H, M)
+        self.f_udt = nn.GRUCell(H + M, H)
+
+    def forward(self, g, x, h):
+        src, dst = g.edges()
+        for _ in range(self._n_rounds):
+            if g.number_of_edges() == 0:
+                c = th.zeros(x.shape[0], self._hidden_size, dtype=x.dtype)
+            else:
+                xh = th.cat((x, h.detach()), 1)
+                m = self.f_msg(th.cat((xh.index_select(0, src), xh.index_select(0, dst)), 1))
+                c = _segment_mean(dst, m, x.shape[0])
+            h = self.f_udt(th.cat((x, c), 1), h)
+        return h
+
+
 class GnnAgent(nn.Module):
-    """Reference MADRQN ``GnnAgent`` (``gnn_agents.py:12-56``) for ``c in {None, 'tarmac', 'base', 'commnet'}``."""
+    """Reference MADRQN ``GnnAgent`` (``gnn_agents.py:12-56``), every comm protocol of ``:27-41``."""
 
     def __init__(self, obs_shape, n_actions, args):
         super().__init__()
@@ -288,6 +365,10 @@ class GnnAgent(nn.Module):
             self.f_comm = BaseComm(args)
         elif self._comm_protocol == "commnet":
             self.f_comm = CommNet(args)
+        elif self._comm_protocol == "disc":
+            self.f_comm = DiscreteComm(args)
+        elif self._comm_protocol == "econv":
+            self.f_comm = EdgeConv(args)
         else:
             raise KeyError("Unsupported communication scheme.")
         self.f_out = DuelingLayer(self._hidden_size, n_actions) if args.dueling else nn.Linear(self._hidden_size, n_actions)
@@ -323,9 +404,11 @@ class DrqnGnnAgent(nn.Module):
 
 
 # ============================================================================================== learner math
-def bptt_loss(policy, target, obs_seq, h0, h0_targ, acts, rews, dones, gamma, double_q, n_agents):
-    """Loss of reference ``MultiAgentQLearner.update`` (``algos/madrqn/learner.py:118-154``, no mixer):
-    ``obs_seq`` has T+1 batched graphs; ``acts (T,N,1)``, ``rews (T,B,n_agents|1)``, ``dones (T,B,1)``."""
+def bptt_loss(policy, target, obs_seq, h0, h0_targ, acts, rews, dones, gamma, double_q, n_agents, mixer=None,
+              target_mixer=None, states=None):
+    """Loss of reference ``MultiAgentQLearner.update`` (``algos/madrqn/learner.py:118-154``): ``obs_seq`` has T+1
+    batched graphs; ``acts (T,N,1)``, ``rews (T,B,n_agents|1)``, ``dones (T,B,1)``; with QMIX (``:144-148``) ``states
+    (T+1,B,S)`` and the two mixers turn the per-agent values into ``Q_tot``."""
     T = len(obs_seq) - 1
     h, h_targ = h0, h0_targ
     agent_out, target_out = [], []
@@ -347,6 +430,9 @@ def bptt_loss(policy, target, obs_seq, h0, h0_targ, acts, rews, dones, gamma, do
     B = rews.shape[1]
     qvals = qvals.view(T, B, n_agents)
     next_vals = next_vals.view(T, B, n_agents)
+    if mixer is not None:
+        qvals = mixer(qvals, states[:-1])
+        next_vals = target_mixer(next_vals, states[1:])
     rews, dones = rews.expand_as(next_vals), dones.expand_as(next_vals)
     target_q = rews + gamma * (1 - dones) * next_vals
     return F.mse_loss(qvals, target_q), qvals

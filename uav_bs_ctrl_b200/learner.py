@@ -427,3 +427,8 @@ class QLearner(MultiAgentQLearner):
     def act(self, obs, h, eps_thres):
         acts, h = super().act(obs, h, eps_thres)
         return (acts[0] if isinstance(acts, list) else acts), h
+
+    def cache(self, obs, h, act, rew, next_obs, next_h, done, bad_mask):
+        """Reference ``algos/drqn/learner.py:67-73``: the DRQN loop (``algos/drqn/run.py:82``) passes 8 arguments —
+        no global state."""
+        super().cache(obs, h, None, act, rew, next_obs, next_h, None, done, bad_mask)

@@ -226,10 +226,36 @@ class BaseComm(nn.Module):
         return self.f_udt(th.cat((x, c), 1), h)
 
 
+def _first_max_by_dst(g, msg, n):
+    """``nodes.mailbox['m'].max(1)[0]`` of the reference's UDF reduce (``gnn_agents.py:176-179``) for per-EDGE messages
+    ``msg (E, F)`` in edge-id order: element-wise max over the in-edges of every destination, zeros where there are
+    none, and — like ``torch.max(dim)`` on the degree-bucketed mailbox — the gradient goes to ONE winner per
+    (destination, feature): the first maximal entry in mailbox (= edge-id) order."""
+    src, dst = g.edges()
+    E, F_ = msg.shape
+    if E == 0:
+        return th.zeros(n, F_, dtype=msg.dtype, device=msg.device)
+    order = th.sort(dst, stable=True)[1]                       # mailbox order: a destination's in-edges by edge id
+    d_sorted = dst[order]
+    deg = th.bincount(dst, minlength=n)
+    start = th.cumsum(deg, 0) - deg
+    slot = th.arange(E, device=dst.device) - start[d_sorted]
+    dmax = int(deg.max())
+    box = th.full((n, dmax, F_), float("-inf"), dtype=msg.dtype, device=msg.device)
+    box = box.index_put((d_sorted, slot), msg[order])
+    top = box.detach().max(1, keepdim=True)[0]
+    is_top = box.detach() == top
+    first = is_top & (th.cumsum(is_top, 1) == 1)               # exactly one winner per (destination, feature)
+    out = th.where(first, box, th.zeros_like(box)).sum(1)
+    return th.where((deg > 0).unsqueeze(1), out, th.zeros_like(out))
+
+
 class DiscreteComm(nn.Module):
     """Reference ``gnn_agents.py:151-193``: 2-digit one-hot bits via hard Gumbel-softmax (tau=0.5) on every edge,
-    element-wise OR (max) over in-edges, ``f_dec``, GRU.  Noise comes from the torch RNG, per edge, as in the
-    reference's edge UDF."""
+    element-wise OR (max) over in-edges, ``f_dec``, GRU.  Noise comes from the torch RNG, per edge in edge-id order, as in
+    the reference's edge UDF (``exponential_feed``: optional iterator of pre-drawn ``Exponential(1)`` tensors
+    ``(E, msg, 2)``, one per call — how the parity tests replay the noise the reference consumed).  The encoder is
+    applied per SOURCE NODE (``f_enc`` sees only the source's ``[x ‖ h]``), the noise per edge."""
 
     def __init__(self, args):
         super().__init__()
@@ -237,18 +263,24 @@ class DiscreteComm(nn.Module):
         self.f_enc = nn.Linear(2 * self._hidden_size, 2 * self._msg_size)
         self.f_dec = nn.Linear(2 * self._msg_size, 2 * self._msg_size)
         self.f_udt = GRUCell(self._hidden_size + 2 * self._msg_size, self._hidden_size)
+        self.exponential_feed = None
 
     def forward(self, g, x, h):
-        n = x.shape[0]
+        n, M = x.shape[0], self._msg_size
         if g.number_of_edges() == 0:
-            c = th.zeros(n, 2 * self._msg_size, device=x.device)
+            c = th.zeros(n, 2 * M, device=x.device)
         else:
-            src, dst = g.edges()
-            logits = self.f_enc(th.cat((x, h.detach()), 1).index_select(0, src))
-            m = F.gumbel_softmax(logits.view(-1, self._msg_size, 2), tau=0.5, hard=True).flatten(1)
-            idx = dst.view(-1, 1).expand_as(m)
-            c = th.zeros(n, m.shape[1], dtype=m.dtype, device=m.device).scatter_reduce(0, idx, m, "amax",
-                                                                                       include_self=False)
+            src, _ = g.edges()
+            logits = self.f_enc(th.cat((x, h.detach()), 1)).index_select(0, src).view(-1, M, 2)
+            if self.exponential_feed is not None:
+                e = next(self.exponential_feed).to(logits.dtype)
+            else:
+                e = th.empty_like(logits).exponential_()
+            # F.gumbel_softmax(logits, tau=0.5, hard=True) with the noise made explicit (straight-through one-hot)
+            y_soft = ((logits - e.log()) / 0.5).softmax(-1)
+            y_hard = th.zeros_like(y_soft).scatter_(-1, y_soft.argmax(-1, keepdim=True), 1.0)
+            m = (y_hard - y_soft.detach() + y_soft).flatten(1)
+            c = _first_max_by_dst(g, m, n)
         return self.f_udt(th.cat((x, self.f_dec(c)), 1), h)
 
 
@@ -272,7 +304,11 @@ class CommNet(nn.Module):
 
 
 class EdgeConv(nn.Module):
-    """Reference ``gnn_agents.py:274-299``: message ``f_msg([x_u ‖ h_u ‖ x_v ‖ h_v])`` (h detached), mean, GRU."""
+    """Reference ``gnn_agents.py:274-299``: message ``f_msg([x_u ‖ h_u ‖ x_v ‖ h_v])`` (h detached), mean, GRU.
+
+    The message is linear in its source and destination halves, so the mean over in-edges is
+    ``W_src · mean_u([x_u ‖ h_u]) + W_dst · [x_v ‖ h_v] + b`` (zero for destinations without in-edges): ONE block-mean
+    launch on the node features + one library GEMM instead of a per-edge ``4H``-wide projection."""
 
     def __init__(self, args):
         super().__init__()
@@ -285,9 +321,9 @@ class EdgeConv(nn.Module):
             if g.number_of_edges() == 0:
                 c = th.zeros(x.shape[0], self._hidden_size, device=x.device)
             else:
-                src, dst = g.edges()
                 xh = th.cat((x, h.detach()), 1)
-                c = _mean_by_dst(g, self.f_msg(th.cat((xh.index_select(0, src), xh.index_select(0, dst)), 1)), x.shape[0])
+                has_in = (g.in_degrees() > 0).unsqueeze(1).to(xh.dtype)
+                c = self.f_msg(th.cat((_mean_of_sources(g, xh), xh), 1)) * has_in
             h = self.f_udt(th.cat((x, c), 1), h)
         return h
 

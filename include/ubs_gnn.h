@@ -203,6 +203,31 @@ UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int Fin, int fl
  * shared memory with bulk async copies (TMA) one layer ahead of the GEMM that consumes them, 0 if it streams weights
  * through registers (the configuration does not fit 227 KB, or UBS_ACT_TMA=0). */
 UBS_API int ubs_agent_act_uses_tma(int H, int M, int K, int A, int U, int Fin, int flags);
+/* ---- Act vector-step as ONE kernel: observation relations + agent step ------------------------------------------
+ * ubs_agent_act_fwd with the two GATv2 star relations of GraphObservationEncoder (gnn_agents.py:92-97,103-104:
+ * 'seen' gt->agent, 'near' ubs->agent) folded in, i.e. everything learner.act (algos/madrqn/learner.py:69-80) runs
+ * per env step: GnnAgent.forward + argmax + epsilon-greedy.  The relations are read straight from an observation
+ * packet: x_gt (rows, F_gt) / x_ubs (rows, F_ubs) compacted source rows in star layout (row id == CSR slot), ip_seen /
+ * ip_near (n_rows + 1) cumulative in-degrees, x_agent (n_rows, F_d).  A CTA owns 16 consecutive agent rows whose source
+ * rows are one contiguous range, staged into shared memory by bulk async copies (TMA); cap_gt / cap_ubs = the largest
+ * possible in-degree (G, U-1), which sizes the staging area.  relpack = the per-relation constant tables of
+ * ubs_gatv2_rel_pack ('seen' then 'near', ubs_gatv2_rel_pack_size floats each), rebuilt whenever a parameter of the
+ * relation encoders changes.  packed / relpack / x_gt / x_ubs must be 16-byte aligned.
+ * ubs_agent_act_rel_supported: 1 when the configuration fits the kernel (H = 32/64-class configs whose weights fit
+ * 227 KB), else 0 — the caller then runs ubs_gatv2_seg_fwd x 2 + ubs_agent_act_fwd.                                   */
+UBS_API int64_t ubs_gatv2_rel_pack_size(int heads, int D);
+UBS_API int ubs_gatv2_rel_pack(const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                               const float* attn, const float* W_res, const float* b_res, int F_s, int F_d, int heads,
+                               int D, float negative_slope, int flags, float* out, void* stream);
+UBS_API int ubs_agent_act_rel_supported(int H, int M, int K, int A, int U, int flags, int heads, int F_gt, int cap_gt,
+                                        int F_ubs, int cap_ubs, int F_d);
+UBS_API int ubs_agent_act_rel_fwd(int H, int M, int K, int A, int U, int flags, const float* packed, const float* relpack,
+                                  const float* x_gt, const int32_t* ip_seen, int F_gt, int cap_gt,
+                                  const float* x_ubs, const int32_t* ip_near, int F_ubs, int cap_ubs,
+                                  const float* x_agent, int F_d, int heads, int gat_flags,
+                                  const float* h0, const uint32_t* mask, float* h_out, float* q, int64_t* actions,
+                                  const float* eg_u, const int64_t* eg_a, const float* eg_eps, int64_t n_rows,
+                                  void* stream);
 /* Reverse-time walk.  dq (n_steps,n_rows,A) and dh_last (n_rows,H, nullable) come from the loss; outputs:
  * d_xin (n_steps,n_rows,Fin), d_h0 (nullable) and the stashes st_dgi/st_dgh (.., 3H), st_dvsq (.., round4(M+2K)),
  * st_dpre (.., H) from which the caller forms the parameter gradients with batched GEMMs over the whole sequence. */

@@ -53,6 +53,11 @@ _PROTOS = {
     "ubs_agent_seq_fwd": (C.c_int, [_int] * 7 + [_F] * 11 + [_i64, _int, _ptr]),
     "ubs_agent_act_fwd": (C.c_int, [_int] * 7 + [_F] * 14 + [_i64, _int, _ptr]),
     "ubs_agent_seq_bwd": (C.c_int, [_int] * 7 + [_F] * 15 + [_i64, _int, _ptr]),
+    "ubs_gatv2_rel_pack_size": (_i64, [_int, _int]),
+    "ubs_gatv2_rel_pack": (C.c_int, [_F] * 7 + [_int] * 4 + [_flt, _int, _F, _ptr]),
+    "ubs_agent_act_rel_supported": (C.c_int, [_int] * 12),
+    "ubs_agent_act_rel_fwd": (C.c_int, [_int] * 6 + [_F, _F, _F, _I, _int, _int, _F, _I, _int, _int, _F, _int, _int, _int]
+                              + [_F] * 8 + [_i64, _ptr]),
     # include/ubs_env.h (config / state / packet structs travel by host pointer)
     "ubs_env_scratch_words": (_i64, [_ptr, _i64]),
     "ubs_env_phase_clocks": (C.c_int, [_ptr]),

@@ -359,6 +359,8 @@ class GnnAgent(nn.Module):
         self._msg_size, self._key_size = getattr(args, "msg_size", 0), getattr(args, "key_size", 0)
         self._n_rounds = getattr(args, "n_rounds", 1)
         self._pack_cache = {}
+        self._relpack_cache = None
+        self.use_rel_act = True       # act step with the two observation relations folded into the act kernel (one launch)
         self.use_seq2 = True          # resident-weight sequence kernels when they fit (False: weight-streaming kernels)
         self.use_seq2_act = False     # act step through the resident-weight kernel (T = 1) instead of the streaming one
 
@@ -405,6 +407,47 @@ class GnnAgent(nn.Module):
             self._pack_cache[dims.ints()] = (key, buf)
             return buf
         return hit[1]
+
+    def _relpacked(self):
+        """Constant tables of the two observation relations for the fused act step, rebuilt (in place) when a parameter
+        of the relation encoders changed."""
+        convs = (self.enc.f_conv["seen"], self.enc.f_conv["near"])
+        ps = [(c.fc_src.weight, c.fc_src.bias, c.fc_dst.weight, c.fc_dst.bias, c.attn, c.res_fc.weight, c.res_fc.bias)
+              for c in convs]
+        key = tuple((t.data_ptr(), t._version) for p in ps for t in p)
+        hit = self._relpack_cache
+        if hit is None or hit[0] != key:
+            c0 = convs[0]
+            buf = ops.gatv2_rel_pack(ps, [c._in_src_feats for c in convs], c0._in_dst_feats, c0._num_heads, c0._out_feats,
+                                     c0._negative_slope, ops.GAT_RESIDUAL | ops.GAT_RELU, None if hit is None else hit[1])
+            self._relpack_cache = hit = (key, buf)
+        return hit[1]
+
+    def rel_act_supported(self, arena):
+        """Whether ``arena_step`` runs as ONE kernel (relations + agent step) for this agent on this arena layout."""
+        dims = self.arena_dims(arena)
+        if dims is None or not self.use_rel_act or not isinstance(self.enc, GraphObservationEncoder):
+            return False
+        L, c0 = arena.layout, self.enc.f_conv["seen"]
+        return ops.agent_act_rel_supported(dims, c0._num_heads, L.F_gt, L.G, L.F_ubs, max(L.U - 1, 0), L.F_ag)
+
+    def refresh_packed(self, arena=None):
+        """Re-packs (in place) every act-step weight buffer built so far if a parameter changed since — a version check
+        when nothing did.  Captured CUDA graphs read these buffers by address, so the learner calls this before every
+        graph replay and after everything that writes parameters (optimizer step, polyak update, ``load_checkpoint``).
+        With ``arena``: also builds the buffers that arena's act step needs (must exist before a capture starts)."""
+        params = None
+        for ints in list(self._pack_cache):
+            params = params or self._fused_params()
+            self._packed(ops.AgentDims(*ints), params)
+        if self._relpack_cache is not None:
+            self._relpacked()
+        if arena is not None:
+            dims = self.arena_dims(arena)
+            if dims is not None:
+                self._packed(dims, params or self._fused_params())
+                if self.rel_act_supported(arena):
+                    self._relpacked()
 
     def _encode_pre(self, g):
         """Input of the fused step: ``[x_gt ‖ x_ubs]`` for the graph encoder (aggregator fused), else the encoder output."""
@@ -501,8 +544,16 @@ class GnnAgent(nn.Module):
         returns the Q values.  Three launches (two relations + the fused step), no allocation-dependent host logic,
         so the call can be captured in a CUDA graph."""
         dims = self.arena_dims(arena)
-        xin = self._arena_xin(arena, t, 1) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t, 1)
         mask = arena.sec("mask", t) if dims.tarmac else None
+        if self.rel_act_supported(arena) and not (self.use_seq2_act and self.use_seq2):
+            L, c0 = arena.layout, self.enc.f_conv["seen"]
+            q = q_out.view(L.N, dims.A) if q_out is not None else th.empty(L.N, dims.A, dtype=th.float32, device=arena.device)
+            ops.agent_act_rel(dims, self._packed(dims, self._fused_params()), self._relpacked(), arena.ptr("x_gt", t),
+                              arena.ptr("ip_seen", t), L.F_gt, L.G, arena.ptr("x_ubs", t), arena.ptr("ip_near", t), L.F_ubs,
+                              max(L.U - 1, 0), arena.ptr("x_agent", t), L.F_ag, c0._num_heads,
+                              ops.GAT_RESIDUAL | ops.GAT_RELU, arena.h[t], mask, arena.h[t + 1], q, arena.acts[t], explore)
+            return q
+        xin = self._arena_xin(arena, t, 1) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t, 1)
         if self.use_seq2_act and self.use_seq2 and ops.seq2_supported(dims):
             # two small library GEMMs (aggregator; fused [pv | pg]) + the resident-weight kernel with T = 1 + Q head
             q, h_all = ops.agent_seq2_infer(dims, self._fused_params(), xin, arena.h[t], mask)

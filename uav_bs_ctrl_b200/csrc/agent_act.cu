@@ -10,6 +10,16 @@
 //     layer i   :  wait(mbar[i & 1])  ->  GEMM from buf[i & 1]
 //     meanwhile :  bulk copy of layer i+1 into buf[(i+1) & 1]   (free since layer i-1 finished)
 // 16 warps per CTA (512 threads), thread tile 4x4, split-K for the narrow layers.
+//
+// Fused observation relations (ubs_agent_act_rel_fwd): the two GATv2 star relations of GraphObservationEncoder
+// (gnn_agents.py:92-97,103-104 -> dglnn.GATv2Conv) run INSIDE this kernel instead of as two launches in front of it.
+// A CTA owns 16 consecutive agent rows; in the star layout their source rows are ONE contiguous range of the
+// observation packet (rows [indptr[row0], indptr[row0 + 16])), so the neighbour lists of the tile are staged with one
+// bulk async copy (TMA) per relation into the shared-memory buffer of the second weight layer — idle until the
+// aggregator GEMM starts — next to the per-relation weight tables that ubs_gatv2_rel_pack precomputes once per
+// parameter update.  One warp per destination row: lanes own edges (online softmax per lane, merged by shuffles),
+// the result lands in the feature-major input tile of the aggregator GEMM: no xin round trip through HBM, no
+// fork / join of relation streams, one launch per vector-step.
 #include "agent_step.cuh"
 
 namespace ubs {
@@ -39,6 +49,170 @@ __device__ __forceinline__ void bulk_load(float* dst, const float* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- fused relations
+// Tables of one relation (ubs_gatv2_rel_pack): wA[H] = W_src row (zero padded to 4), wR[H] = {W_res[0], W_res[1],
+// b_res, b_src}, wD[H] = {W_dst[0], W_dst[1], b_src + b_dst, (1-s)/2 attn}, hP[heads][8] = (1+s)/2 sum_d attn *
+// {W_src[0..3] | W_dst[0..1], b_src + b_dst, 0}: the same constants gatv2_fwd_kernel derives in its prologue.
+__host__ __device__ inline int rel_table_floats(int H, int heads) { return 12 * H + 8 * heads; }
+
+struct RelSmem { int tabs, xs[2], cbuf, ips, xd, total; };     // float offsets inside the staging region
+__host__ __device__ inline RelSmem rel_smem(const StepDims& d, const RelIn& r) {
+    RelSmem s;
+    int o = 0;
+    auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
+    s.tabs = take(2 * rel_table_floats(d.H, r.heads));
+    s.xs[0] = take(R * r.cap[0] * r.FS[0] + 4);
+    s.xs[1] = take(R * r.cap[1] * r.FS[1] + 4);
+    s.cbuf = take((NT / 32) * 2 * d.H);
+    s.ips = take(2 * (R + 1));
+    s.xd = take(2 * R);
+    s.total = o;
+    return s;
+}
+
+template <int FS>
+__device__ __forceinline__ void lds_row(const float* p, float (&x)[FS]) {
+    if constexpr (FS == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else if constexpr (FS == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        x[0] = t.x; x[1] = t.y;
+    } else {
+#pragma unroll
+        for (int f = 0; f < FS; ++f) x[f] = p[f];
+    }
+}
+
+// One warp, one destination: GATv2 over the source rows xs[beg .. end) (shared memory), result -> out[ch * RP].
+// Same arithmetic as gatv2_fwd_kernel (GS = 32 lanes per destination, two edges per lane per pass).
+template <int FS, int HEADS>
+__device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, const float* tab, int D, float xv0, float xv1,
+                                         int flags, float2* cbuf, float* out) {
+    constexpr int HPW = HEADS >= 2 ? 2 : 1;        // heads per pass over the edges (register budget of a 512-thread CTA)
+    const int H = HEADS * D, lane = threadIdx.x & 31;
+    const float4* wA = reinterpret_cast<const float4*>(tab);
+    const float4* wR = wA + H;
+    const float4* wD = wR + H;
+    const float* hP = reinterpret_cast<const float*>(wD + H);
+    const bool relu = flags & UBS_GAT_RELU, has_res = flags & UBS_GAT_RESIDUAL;
+    for (int ch = lane; ch < H; ch += 32) {
+        const float4 w = wD[ch];
+        cbuf[ch] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
+    }
+    __syncwarp();
+    for (int k0 = 0; k0 < HEADS; k0 += HPW) {
+        float lin[HPW], m[HPW], l[HPW], acc[HPW][FS];
+#pragma unroll
+        for (int k = 0; k < HPW; ++k) {
+            lin[k] = fmaf(hP[(k0 + k) * 8 + 5], xv1, fmaf(hP[(k0 + k) * 8 + 4], xv0, hP[(k0 + k) * 8 + 6]));
+            m[k] = -CUDART_INF_F; l[k] = 0.f;
+#pragma unroll
+            for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
+        }
+        for (int e = beg + lane; e < end; e += 64) {
+            float x[2][FS];
+            bool ok[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ej = e + j * 32;
+                ok[j] = ej < end;
+                if (ok[j]) lds_row<FS>(xs + ej * FS, x[j]);
+                else {
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) x[j][f] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < HPW; ++k) {
+                const float4* wk = wA + (k0 + k) * D;
+                const float2* ck = cbuf + (k0 + k) * D;
+                const float4 pk = *reinterpret_cast<const float4*>(hP + (k0 + k) * 8);
+                float sc2[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    sc2[j] = fmaf(pk.x, x[j][0], lin[k]);
+                    if constexpr (FS > 1) sc2[j] = fmaf(pk.y, x[j][1], sc2[j]);
+                    if constexpr (FS > 2) sc2[j] = fmaf(pk.z, x[j][2], sc2[j]);
+                    if constexpr (FS > 3) sc2[j] = fmaf(pk.w, x[j][3], sc2[j]);
+                }
+#pragma unroll 8
+                for (int dd = 0; dd < D; ++dd) {
+                    const float4 w = wk[dd];
+                    const float2 c = ck[dd];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float z = c.x;
+                        z = fmaf(w.x, x[j][0], z);
+                        if constexpr (FS > 1) z = fmaf(w.y, x[j][1], z);
+                        if constexpr (FS > 2) z = fmaf(w.z, x[j][2], z);
+                        if constexpr (FS > 3) z = fmaf(w.w, x[j][3], z);
+                        sc2[j] = fmaf(c.y, fabsf(z), sc2[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (ok[j]) {
+                        const float mn = fmaxf(m[k], sc2[j]);
+                        const float sc = __expf(m[k] - mn);
+                        const float p = __expf(sc2[j] - mn);
+                        l[k] = fmaf(l[k], sc, p);
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[j][f]);
+                        m[k] = mn;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HPW; ++k) {
+            const float Mx = warp_max(m[k]);
+            const float sc = (m[k] == -CUDART_INF_F) ? 0.f : __expf(m[k] - Mx);
+            l[k] = warp_sum(l[k] * sc);
+#pragma unroll
+            for (int f = 0; f < FS; ++f) acc[k][f] = warp_sum(acc[k][f] * sc);
+            const float inv = l[k] > 0.f ? 1.0f / l[k] : 0.f;
+            for (int dd = lane; dd < D; dd += 32) {
+                const int ch = (k0 + k) * D + dd;
+                const float4 w = wA[ch];
+                const float4 r = wR[ch];
+                float o = 0.f;
+                if (l[k] > 0.f) {
+                    float t = w.x * acc[k][0];
+                    if constexpr (FS > 1) t = fmaf(w.y, acc[k][1], t);
+                    if constexpr (FS > 2) t = fmaf(w.z, acc[k][2], t);
+                    if constexpr (FS > 3) t = fmaf(w.w, acc[k][3], t);
+                    o = fmaf(t, inv, r.w);
+                }
+                if (has_res) o += fmaf(r.y, xv1, fmaf(r.x, xv0, r.z));
+                if (relu) o = fmaxf(o, 0.f);
+                out[ch * RP] = o;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int FS>
+__device__ __forceinline__ void gat_rel_heads(int heads, const float* xs, int beg, int end, const float* tab, int D,
+                                              float xv0, float xv1, int flags, float2* cbuf, float* out) {
+    switch (heads) {
+        case 1: gat_rel_row<FS, 1>(xs, beg, end, tab, D, xv0, xv1, flags, cbuf, out); break;
+        case 2: gat_rel_row<FS, 2>(xs, beg, end, tab, D, xv0, xv1, flags, cbuf, out); break;
+        case 4: gat_rel_row<FS, 4>(xs, beg, end, tab, D, xv0, xv1, flags, cbuf, out); break;
+        default: gat_rel_row<FS, 8>(xs, beg, end, tab, D, xv0, xv1, flags, cbuf, out); break;
+    }
 }
 
 // out[j*RP + r] = act(bias[j] + sum_k W[k*ldw + j] * A[k*RP + r]);  W, bias, A in shared memory.  mode 0 store, 1 relu.
@@ -182,9 +356,11 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
     float* scratch = take(plan.scratch);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o);
 
+    const bool fused_rel = a.rel.relpack != nullptr;
     if (threadIdx.x == 0) {
         mbar_init(bars, 1);
         mbar_init(bars + 1, 1);
+        mbar_init(bars + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -207,7 +383,75 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
 
     for (int t = 0; t < a.T; ++t) {
         int li = 0;                                    // index of the layer about to run
-        load_tile(a.xin + t * a.st_xin, row0, n_valid, d.Fin, d.Fin, ag ? sXin : sX);
+        if (fused_rel) {
+            // ---- the two observation relations, staged into the (still idle) buffer of weight layer 1 ----------------
+            const RelIn& rl = a.rel;
+            const RelSmem rs = rel_smem(d, rl);
+            float* stage = wbuf[1];
+            int* ips = reinterpret_cast<int*>(stage + rs.ips);
+            float* xd = stage + rs.xd;
+            if (threadIdx.x < 2 * (R + 1)) {
+                const int rel = threadIdx.x / (R + 1), i = threadIdx.x - rel * (R + 1);
+                ips[threadIdx.x] = __ldg(rl.indptr[rel] + row0 + min(i, n_valid));
+            } else if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * R) {
+                const int i = threadIdx.x - 64, r = i >> 1, f = i & 1;
+                xd[i] = (r < n_valid && f < rl.F_d) ? __ldg(rl.x_dst + (row0 + r) * rl.F_d + f) : 0.f;
+            }
+            __syncthreads();
+            int shift[2];
+#pragma unroll
+            for (int rel = 0; rel < 2; ++rel) shift[rel] = (ips[rel * (R + 1)] * rl.FS[rel]) & 3;
+            if (threadIdx.x == 0) {
+                // neighbour lists of the tile: rows [ip[row0], ip[row0 + n_valid]) are contiguous in the packet (star layout)
+                uint32_t bytes[2];
+                const float* src[2];
+                const uint32_t tab_bytes = 2u * (uint32_t)rel_table_floats(H, rl.heads) * 4u;
+                uint32_t total = tab_bytes;
+#pragma unroll
+                for (int rel = 0; rel < 2; ++rel) {
+                    const int64_t fbeg = (int64_t)ips[rel * (R + 1)] * rl.FS[rel];
+                    const int64_t fend = (int64_t)ips[rel * (R + 1) + n_valid] * rl.FS[rel];
+                    const int64_t abeg = fbeg & ~(int64_t)3, aend = (fend + 3) & ~(int64_t)3;
+                    src[rel] = rl.x_src[rel] + abeg;
+                    bytes[rel] = fend > fbeg ? (uint32_t)(aend - abeg) * 4u : 0u;
+                    total += bytes[rel];
+                }
+                mbar_expect(bars + 2, total);
+                bulk_copy(stage + rs.tabs, rl.relpack, tab_bytes, bars + 2);
+#pragma unroll
+                for (int rel = 0; rel < 2; ++rel)
+                    if (bytes[rel]) bulk_copy(stage + rs.xs[rel], src[rel], bytes[rel], bars + 2);
+            }
+            mbar_wait(bars + 2, 0);
+            {
+                const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;      // warp = destination row of the tile
+                float2* cb = reinterpret_cast<float2*>(stage + rs.cbuf) + r * H;
+                const int D = H / rl.heads;
+#pragma unroll
+                for (int rel = 0; rel < 2; ++rel) {
+                    float* out = sXin + rel * H * RP + r;
+                    if (r < n_valid) {
+                        const int b0 = ips[rel * (R + 1)];
+                        const int beg = ips[rel * (R + 1) + r] - b0, end = ips[rel * (R + 1) + r + 1] - b0;
+                        const float* xs = stage + rs.xs[rel] + shift[rel];
+                        const float* tab = stage + rs.tabs + rel * rel_table_floats(H, rl.heads);
+                        switch (rl.FS[rel]) {
+                            case 1: gat_rel_heads<1>(rl.heads, xs, beg, end, tab, D, xd[2 * r], xd[2 * r + 1], rl.gat_flags, cb, out); break;
+                            case 2: gat_rel_heads<2>(rl.heads, xs, beg, end, tab, D, xd[2 * r], xd[2 * r + 1], rl.gat_flags, cb, out); break;
+                            case 3: gat_rel_heads<3>(rl.heads, xs, beg, end, tab, D, xd[2 * r], xd[2 * r + 1], rl.gat_flags, cb, out); break;
+                            default: gat_rel_heads<4>(rl.heads, xs, beg, end, tab, D, xd[2 * r], xd[2 * r + 1], rl.gat_flags, cb, out); break;
+                        }
+                    } else {
+                        for (int ch = lane; ch < H; ch += 32) out[ch * RP] = 0.f;
+                    }
+                }
+            }
+            __syncthreads();
+            // the staging region is about to be overwritten by a bulk copy (async proxy) after generic-proxy accesses
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        } else {
+            load_tile(a.xin + t * a.st_xin, row0, n_valid, d.Fin, d.Fin, ag ? sXin : sX);
+        }
         __syncthreads();
         if (ag) {
             issue(li + 1);
@@ -310,6 +554,17 @@ bool agent_act_fits(const StepDims& d) {
     return true;
 }
 
+// The fused-relation prologue stages tables + neighbour lists in the buffer of weight layer 1.
+static bool agent_act_rel_fits(const StepDims& d, const RelIn& r) {
+    if (!d.aggr() || d.Fin != 2 * d.H || !agent_act_fits(d)) return false;
+    if (r.heads != 1 && r.heads != 2 && r.heads != 4 && r.heads != 8) return false;
+    if (d.H % r.heads || r.F_d < 1 || r.F_d > 2) return false;
+    for (int i = 0; i < 2; ++i)
+        if (r.FS[i] < 1 || r.FS[i] > 4 || r.cap[i] < 0) return false;
+    const act::Plan plan = act::make_plan(d);
+    return act::rel_smem(d, r).total <= plan.capB;
+}
+
 int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled) {
     *handled = false;
     if (a.sv_gate != nullptr) return 0;                // training saves: streaming / resident-weight kernels
@@ -317,10 +572,13 @@ int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled) {
     if (!agent_act_fits(a.d)) return 0;
     const act::Plan plan = act::make_plan(a.d);
     const size_t smem = act::smem_bytes(plan);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(act::agent_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    // every configuration that fits needs more than the 48 KB default: opt in to the device maximum once per
+    // process (idempotent, so a racing second thread only repeats the same call)
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(act::agent_act_kernel,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_rc != cudaSuccess) {
+        set_error("ubs_agent_act_fwd: cannot opt in to 227 KB of shared memory: %s", cudaGetErrorString(attr_rc));
+        return 1;
     }
     const int rpt = a.d.rows_per_tile();
     const unsigned grid = (unsigned)((a.N + rpt - 1) / rpt);
@@ -329,4 +587,113 @@ int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled) {
     return check_launch("ubs_agent_act_fwd(tma)");
 }
 
+// ---------------------------------------------------------------------------------------------- relation tables
+struct RelPackArgs {
+    const float *W_src, *b_src, *W_dst, *b_dst, *attn, *W_res, *b_res;
+    int FS, FD, heads, D, flags; float slope; float* out;
+};
+
+__global__ void __launch_bounds__(256) gatv2_rel_pack_kernel(const RelPackArgs a) {
+    const int H = a.heads * a.D;
+    float4* wA = reinterpret_cast<float4*>(a.out);
+    float4* wR = wA + H;
+    float4* wD = wR + H;
+    float* hP = reinterpret_cast<float*>(wD + H);
+    for (int ch = threadIdx.x; ch < H; ch += 256) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int f = 0; f < a.FS; ++f) w[f] = a.W_src[ch * a.FS + f];
+        wA[ch] = make_float4(w[0], w[1], w[2], w[3]);
+        const float bs = a.b_src ? a.b_src[ch] : 0.f;
+        const float bd = a.b_dst ? a.b_dst[ch] : 0.f;
+        float r0 = 0.f, r1 = 0.f, rb = 0.f;
+        if (a.flags & UBS_GAT_RESIDUAL) {
+            r0 = a.W_res[ch * a.FD];
+            r1 = a.FD > 1 ? a.W_res[ch * a.FD + 1] : 0.f;
+            rb = a.b_res ? a.b_res[ch] : 0.f;
+        }
+        wR[ch] = make_float4(r0, r1, rb, bs);
+        wD[ch] = make_float4(a.W_dst[ch * a.FD], a.FD > 1 ? a.W_dst[ch * a.FD + 1] : 0.f, bs + bd,
+                             0.5f * (1.0f - a.slope) * a.attn[ch]);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.heads * 8) {
+        const int k = threadIdx.x / 8, j = threadIdx.x % 8;
+        float acc = 0.f;
+        for (int d0 = 0; d0 < a.D; ++d0) {
+            const int ch = k * a.D + d0;
+            const float at = a.attn[ch];
+            float w = 0.f;
+            if (j < 4) w = j == 0 ? wA[ch].x : j == 1 ? wA[ch].y : j == 2 ? wA[ch].z : wA[ch].w;
+            else if (j == 4) w = wD[ch].x;
+            else if (j == 5) w = wD[ch].y;
+            else if (j == 6) w = wD[ch].z;
+            acc = fmaf(at, w, acc);
+        }
+        hP[threadIdx.x] = 0.5f * (1.0f + a.slope) * acc;
+    }
+}
+
 }  // namespace ubs
+
+extern "C" UBS_API int64_t ubs_gatv2_rel_pack_size(int heads, int D) { return ubs::act::rel_table_floats(heads * D, heads); }
+
+extern "C" UBS_API int ubs_gatv2_rel_pack(const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                                          const float* attn, const float* W_res, const float* b_res, int F_s, int F_d,
+                                          int heads, int D, float negative_slope, int flags, float* out, void* stream) {
+    UBS_REQUIRE(W_src && W_dst && attn && out, "ubs_gatv2_rel_pack: NULL argument");
+    UBS_REQUIRE(F_s >= 1 && F_s <= 4 && F_d >= 1 && F_d <= 2 && heads >= 1 && heads <= 8 && D >= 1,
+                "ubs_gatv2_rel_pack: shape outside the fused relation kernels (F_s <= 4, F_d <= 2, heads <= 8)");
+    UBS_REQUIRE(!(flags & UBS_GAT_RESIDUAL) || W_res, "ubs_gatv2_rel_pack: residual weights missing");
+    UBS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "ubs_gatv2_rel_pack: out must be 16-byte aligned");
+    ubs::RelPackArgs a{W_src, b_src, W_dst, b_dst, attn, W_res, b_res, F_s, F_d, heads, D, flags, negative_slope, out};
+    ubs::gatv2_rel_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    return ubs::check_launch("ubs_gatv2_rel_pack");
+}
+
+static ubs::RelIn mk_rel(const float* relpack, const float* x_gt, const int32_t* ip_seen, int F_gt, int cap_gt,
+                         const float* x_ubs, const int32_t* ip_near, int F_ubs, int cap_ubs, const float* x_agent, int F_d,
+                         int heads, int gat_flags) {
+    ubs::RelIn r{};
+    r.relpack = relpack;
+    r.x_src[0] = x_gt; r.indptr[0] = ip_seen; r.FS[0] = F_gt; r.cap[0] = cap_gt;
+    r.x_src[1] = x_ubs; r.indptr[1] = ip_near; r.FS[1] = F_ubs; r.cap[1] = cap_ubs;
+    r.x_dst = x_agent; r.F_d = F_d; r.heads = heads; r.gat_flags = gat_flags;
+    return r;
+}
+
+extern "C" UBS_API int ubs_agent_act_rel_supported(int H, int M, int K, int A, int U, int flags, int heads, int F_gt,
+                                                   int cap_gt, int F_ubs, int cap_ubs, int F_d) {
+    const ubs::StepDims d = ubs::mk_dims(H, M, K, A, U, 2 * H, flags);
+    const ubs::RelIn r = mk_rel(nullptr, nullptr, nullptr, F_gt, cap_gt, nullptr, nullptr, F_ubs, cap_ubs, nullptr, F_d, heads, 0);
+    return ubs::agent_act_rel_fits(d, r) ? 1 : 0;
+}
+
+extern "C" UBS_API int ubs_agent_act_rel_fwd(int H, int M, int K, int A, int U, int flags, const float* packed,
+                                             const float* relpack, const float* x_gt, const int32_t* ip_seen, int F_gt,
+                                             int cap_gt, const float* x_ubs, const int32_t* ip_near, int F_ubs, int cap_ubs,
+                                             const float* x_agent, int F_d, int heads, int gat_flags, const float* h0,
+                                             const uint32_t* mask, float* h_out, float* q, int64_t* actions,
+                                             const float* eg_u, const int64_t* eg_a, const float* eg_eps, int64_t n_rows,
+                                             void* stream) {
+    ubs::StepArgs a{};
+    a.d = ubs::mk_dims(H, M, K, A, U, 2 * H, flags);
+    if (int rc = ubs::check_dims("ubs_agent_act_rel_fwd", a.d)) return rc;
+    UBS_REQUIRE(packed && relpack && x_gt && ip_seen && x_ubs && ip_near && x_agent && h0 && h_out && q,
+                "ubs_agent_act_rel_fwd: NULL argument");
+    UBS_REQUIRE(!a.d.tarmac() || mask, "ubs_agent_act_rel_fwd: TarMAC needs the block mask");
+    UBS_REQUIRE(!a.d.tarmac() || n_rows % a.d.U == 0, "ubs_agent_act_rel_fwd: n_rows must be a multiple of agents per env");
+    UBS_REQUIRE(eg_u == nullptr || (eg_a && eg_eps && actions), "ubs_agent_act_rel_fwd: incomplete epsilon-greedy arguments");
+    a.rel = mk_rel(relpack, x_gt, ip_seen, F_gt, cap_gt, x_ubs, ip_near, F_ubs, cap_ubs, x_agent, F_d, heads, gat_flags);
+    UBS_REQUIRE(ubs::agent_act_rel_fits(a.d, a.rel), "ubs_agent_act_rel_fwd: configuration outside the fused kernel "
+                "(ask ubs_agent_act_rel_supported first)");
+    for (const void* p : {(const void*)packed, (const void*)relpack, (const void*)x_gt, (const void*)x_ubs})
+        UBS_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15u) == 0, "ubs_agent_act_rel_fwd: bulk-copy sources must be 16-byte aligned");
+    if (n_rows == 0) return 0;
+    a.packed = packed; a.h0 = h0; a.mask = mask; a.st_mask = n_rows;
+    a.h_out = h_out; a.st_h = n_rows * H; a.q = q; a.st_q = n_rows * A; a.actions = actions; a.st_act = n_rows;
+    a.eg_u = eg_u; a.eg_a = eg_a; a.eg_eps = eg_eps; a.N = n_rows; a.T = 1;
+    bool handled = false;
+    const int rc = ubs::launch_agent_act(a, (cudaStream_t)stream, &handled);
+    UBS_REQUIRE(handled || rc, "ubs_agent_act_rel_fwd: the fused kernel did not take the launch");
+    return rc;
+}

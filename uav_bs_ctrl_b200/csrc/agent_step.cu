@@ -458,7 +458,7 @@ static int bwd_smem_floats(const StepDims& d) {
     return rows * RP + NT * 16;
 }
 
-static int check_dims(const char* fn, const StepDims& d) {
+int check_dims(const char* fn, const StepDims& d) {
     if (d.H < 16 || d.H % 4 || d.H > 256) { set_error("%s: hidden size %d unsupported (multiple of 4, 16..256)", fn, d.H); return 2; }
     if (d.A < 1 || d.A > 64) { set_error("%s: n_actions %d unsupported", fn, d.A); return 2; }
     if (d.tarmac() && (d.U < 1 || d.U > R)) { set_error("%s: agents per env must be 1..%d for the fused step (got %d)", fn, R, d.U); return 2; }
@@ -467,7 +467,7 @@ static int check_dims(const char* fn, const StepDims& d) {
     return 0;
 }
 
-static StepDims mk_dims(int H, int M, int K, int A, int U, int Fin, int flags) {
+StepDims mk_dims(int H, int M, int K, int A, int U, int Fin, int flags) {
     StepDims d;
     d.H = H; d.M = (flags & UBS_STEP_TARMAC) ? M : 0; d.K = (flags & UBS_STEP_TARMAC) ? K : 0; d.A = A;
     d.U = (flags & UBS_STEP_TARMAC) ? U : 1; d.Fin = Fin; d.flags = flags;

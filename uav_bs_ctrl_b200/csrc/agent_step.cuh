@@ -46,8 +46,21 @@ __host__ __device__ inline PackLayout make_layout(const StepDims& d) {
     return L;
 }
 
+// Observation relations folded into the act step (agent_act.cu): the two GATv2 star relations of
+// GraphObservationEncoder (gnn_agents.py:92-97,103-104) read straight from an observation packet.
+struct RelIn {
+    const float* relpack;        // per-relation tables of ubs_gatv2_rel_pack, relation 0 then relation 1 (NULL: not fused)
+    const float* x_src[2];       // compacted source rows (star layout: row id == CSR slot)
+    const int* indptr[2];        // (n_rows + 1) cumulative in-degrees
+    int FS[2];                   // source feature widths (1..4)
+    int cap[2];                  // max in-degree of a destination (G, U-1): bounds the shared-memory staging area
+    const float* x_dst; int F_d; // (n_rows, F_d) destination (agent) features, F_d <= 2
+    int heads; int gat_flags;    // UBS_GAT_* flags
+};
+
 struct StepArgs {
     StepDims d;
+    RelIn rel;
     const float* packed;
     // forward, sequence-strided: tensor[t] = base + t * stride (strides in floats / elements)
     const float* xin;  int64_t st_xin;      // (T, N, Fin)
@@ -76,5 +89,7 @@ struct StepArgs {
 
 int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled);   // agent_act.cu
 bool agent_act_fits(const StepDims& d);
+StepDims mk_dims(int H, int M, int K, int A, int U, int Fin, int flags);   // agent_step.cu
+int check_dims(const char* fn, const StepDims& d);
 
 }  // namespace ubs

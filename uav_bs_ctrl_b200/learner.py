@@ -15,6 +15,7 @@ Loss math (``learner.py:118-154``), value clipping, AdamW, polyak target and che
 from __future__ import annotations
 
 import random
+import weakref
 from collections import deque
 from copy import deepcopy
 from typing import List
@@ -84,6 +85,7 @@ class MultiAgentQLearner:
         self.target_net.load_state_dict(self.policy_net.state_dict())
         self.target_net.eval()
         self.params = list(self.policy_net.parameters())
+        self._n_policy = sum(p.numel() for p in self.params)
         self.mixer = None
         if getattr(args, "mixer", False):                      # QMIX (reference learner.py:35-40)
             from .agents.mixers import QMixer
@@ -239,7 +241,9 @@ class MultiAgentQLearner:
         loss.backward()
         self.grad_bucket.rebind()
         dist.avg_grads(self.grad_bucket)                                     # DP: one flat all-reduce
-        self.grad_bucket.flat.clamp_(-1.0, 1.0)                              # == clip_grad_value_(params, 1), one launch
+        # clip_grad_value_(self.policy_net.parameters(), 1) (reference learner.py:159): the policy parameters come first in
+        # the flat bucket; the QMIX mixer's gradients stay unclipped like in the reference
+        self.grad_bucket.flat[:self._n_policy].clamp_(-1.0, 1.0)
         self.optimizer.step()
         with th.no_grad():
             pp, tp = list(self.policy_net.parameters()), list(self.target_net.parameters())
@@ -247,9 +251,17 @@ class MultiAgentQLearner:
                 pp, tp = pp + list(self.mixer.parameters()), tp + list(self.target_mixer.parameters())
             th._foreach_mul_(tp, self.polyak)
             th._foreach_add_(tp, pp, alpha=1 - self.polyak)
+        self._refresh_packed()
         if sync:
             return dict(LossQ=loss.item(), QVals=qvals.detach().cpu().numpy())
         return dict(LossQ=loss.detach(), QVals=qvals.detach())
+
+    def _refresh_packed(self):
+        """AdamW / polyak / checkpoint loading wrote the parameters in place: bring the packed act-step copies (read by
+        address from captured CUDA graphs) up to date."""
+        for net in (self.policy_net, self.target_net):
+            if hasattr(net, "refresh_packed"):
+                net.refresh_packed()
 
     # ------------------------------------------------------------------------------------------ sequence-arena path
     def new_arena(self, n_gts, n_slots=None):
@@ -284,20 +296,19 @@ class MultiAgentQLearner:
         """``act`` on arena slot t (observation already staged with ``arena.load``): writes ``arena.h[t+1]`` and the
         ε-greedy actions ``arena.acts[t]`` (returned, on the device).  With ``args.cuda_graphs`` the three kernels and
         the ε-greedy ops of every slot are captured once and replayed."""
-        if not hasattr(self, "_eps_dev"):
-            self._eps_dev = th.zeros((), device=self.device)
-            self._eps_host, self._act_graphs = None, {}
-        if self._eps_host != eps_thres:
-            self._eps_dev.fill_(float(eps_thres))
-            self._eps_host = eps_thres
+        self._set_eps(eps_thres)
         if not getattr(self.args, "cuda_graphs", False):
             self._act_arena_eager(arena, t)
             return arena.acts[t]
-        key = (id(arena), t)
-        g = self._act_graphs.get(key)
+        # captured graphs hold raw device addresses of the arena (and env) they were captured on: the cache lives and
+        # dies with those objects (weak keys) instead of being keyed by id(), which a later object could reuse
+        graphs = self._graph_cache(arena)
+        key = ("act", t)
+        g = graphs.get(key)
+        # packed weights are read by address inside the graph: re-pack (outside any capture) if a parameter changed
+        # since — optimizer step, load_checkpoint, load_state_dict, a replay-buffer update()
+        self.policy_net.refresh_packed(arena)
         if g is None:
-            # parameters must already be packed: the pack kernel must not be part of the captured graph
-            self.policy_net._packed(self.policy_net.arena_dims(arena), self.policy_net._fused_params())
             side = th.cuda.Stream()
             side.wait_stream(th.cuda.current_stream())
             with th.cuda.stream(side):
@@ -308,10 +319,28 @@ class MultiAgentQLearner:
             with th.cuda.graph(g):
                 self._act_arena_eager(arena, t)
             g = (g, _lib.launch_count() - n0)             # library kernels inside the graph (for the launch counter)
-            self._act_graphs[key] = g
+            graphs[key] = g
         g[0].replay()
         _lib.add_launches(g[1])
         return arena.acts[t]
+
+    def _set_eps(self, eps_thres):
+        if not hasattr(self, "_eps_dev"):
+            self._eps_dev = th.zeros((), device=self.device)
+            self._eps_host = None
+        if self._eps_host != eps_thres:
+            self._eps_dev.fill_(float(eps_thres))
+            self._eps_host = eps_thres
+
+    def _graph_cache(self, arena, env=None):
+        if not hasattr(self, "_graphs"):
+            self._graphs = weakref.WeakKeyDictionary()
+        per_arena = self._graphs.setdefault(arena, {})
+        if env is None:
+            return per_arena.setdefault("self", {})
+        if "env" not in per_arena:
+            per_arena["env"] = weakref.WeakKeyDictionary()
+        return per_arena["env"].setdefault(env, {})
 
     def rollout_arena(self, env, arena, eps_thres):
         """One whole episode window on the device env (``envs.MultiUbsCoverageVecEnv``): for t in 0..T-1 the fused act
@@ -321,12 +350,12 @@ class MultiAgentQLearner:
         ``env=None``: the T act steps alone, on observations that are already resident in the arena (replayed
         episodes) — the same graph without the env kernels."""
         T = self.max_seq_len
-        if not hasattr(self, "_eps_dev"):
-            self._eps_dev = th.zeros((), device=self.device)
-            self._eps_host, self._act_graphs = None, {}
-        if self._eps_host != eps_thres:
-            self._eps_dev.fill_(float(eps_thres))
-            self._eps_host = eps_thres
+        if env is not None and T > getattr(env, "episode_limit", T):
+            # the device env flags done at t == episode_limit and never resets itself or the hidden state (the reference
+            # loop does both, run.py:91-94): a longer window would keep stepping a finished episode.  A shorter window is
+            # the prefix of an episode; either way the caller resets the env (and begin_sequence) before every window.
+            raise ValueError(f"rollout_arena: max_seq_len ({T}) exceeds the env's episode_limit ({env.episode_limit})")
+        self._set_eps(eps_thres)
 
         def run():
             for t in range(T):
@@ -338,10 +367,11 @@ class MultiAgentQLearner:
         if not getattr(self.args, "cuda_graphs", False) or ops.TIMER is not None:
             run()
             return
-        key = ("rollout", id(arena), id(env))
-        g = self._act_graphs.get(key)
+        graphs = self._graph_cache(arena, env)
+        key = "rollout"
+        g = graphs.get(key)
+        self.policy_net.refresh_packed(arena)
         if g is None:
-            self.policy_net._packed(self.policy_net.arena_dims(arena), self.policy_net._fused_params())
             snap = env.buf.snapshot() if env is not None else None   # the warm-up step must not advance the episode
             side = th.cuda.Stream()
             side.wait_stream(th.cuda.current_stream())
@@ -357,7 +387,7 @@ class MultiAgentQLearner:
             with th.cuda.graph(g):
                 run()
             g = (g, _lib.launch_count() - n0)
-            self._act_graphs[key] = g
+            graphs[key] = g
         g[0].replay()
         _lib.add_launches(g[1])
 
@@ -377,11 +407,7 @@ class MultiAgentQLearner:
             target_out, _ = self.target_net.arena_sequence(arena, 1, T, h_targ)
         states = arena.states(T + 1) if self.mixer is not None else None
         loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones, states)
-        out = self._optimise(loss, qvals, sync)
-        # refresh the packed weights outside any captured graph (AdamW / polyak updated the parameters in place)
-        for net in (self.policy_net, self.target_net):
-            net._packed(net.arena_dims(arena), net._fused_params())
-        return out
+        return self._optimise(loss, qvals, sync)
 
     # ------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, path, stamp):
@@ -405,6 +431,7 @@ class MultiAgentQLearner:
             self.target_mixer.load_state_dict(self.mixer.state_dict())
         if self.anneal_lr:
             self.lr_scheduler.load_state_dict(checkpoint["lr_scheduler_state_dict"])
+        self._refresh_packed()
         return stamp
 
 

@@ -372,6 +372,47 @@ def agent_seq_infer(dims: AgentDims, packed, xin, h0, mask, want_actions=False, 
     return (q, h_out, acts) if want_actions else (q, h_out)
 
 
+def gatv2_rel_pack(conv_params, F_s, F_d, heads, D, slope, flags, out=None):
+    """Per-relation constant tables of the fused act step (``ubs_gatv2_rel_pack``) for the relations in
+    ``conv_params`` = ``[(W_src, b_src, W_dst, b_dst, attn, W_res, b_res), ...]`` (``F_s`` one width per relation),
+    concatenated into ONE buffer (rebuilt in place when ``out`` is given: captured CUDA graphs keep its address)."""
+    lib = _lib.load()
+    n = int(lib.ubs_gatv2_rel_pack_size(heads, D))
+    dev = conv_params[0][0].device
+    if out is None or out.numel() != n * len(conv_params):
+        out = th.empty(n * len(conv_params), dtype=th.float32, device=dev)
+    for r, (ps, fs) in enumerate(zip(conv_params, F_s)):
+        ptrs = [_lib.ptr(_f32c(p.detach()) if p is not None else None) for p in ps]
+        _lib.check(lib.ubs_gatv2_rel_pack(*ptrs, fs, F_d, heads, D, float(slope), int(flags), out.data_ptr() + 4 * n * r,
+                                          _lib.stream()), "ubs_gatv2_rel_pack")
+    return out
+
+
+def agent_act_rel_supported(dims: "AgentDims", heads, F_gt, cap_gt, F_ubs, cap_ubs, F_d) -> bool:
+    if not (dims.supported() and dims.aggr and dims.Fin == 2 * dims.H):
+        return False
+    return bool(_lib.load().ubs_agent_act_rel_supported(dims.H, dims.M, dims.K, dims.A, dims.U, dims.flags, heads, F_gt, cap_gt,
+                                                        F_ubs, cap_ubs, F_d))
+
+
+def agent_act_rel(dims: "AgentDims", packed, relpack, x_gt_ptr, ip_seen_ptr, F_gt, cap_gt, x_ubs_ptr, ip_near_ptr, F_ubs,
+                  cap_ubs, x_agent_ptr, F_d, heads, gat_flags, h0, mask, h_out, q, acts=None, explore=None):
+    """ONE launch per act vector-step (``ubs_agent_act_rel_fwd``): both GATv2 observation relations read from raw packet
+    addresses + aggregator + TarMAC / GRU + Q head + argmax + epsilon-greedy.  ``h0 (N,H)`` -> ``h_out (N,H)``,
+    ``q (N,A)``, ``acts (N,) int64``; every output is a caller-provided contiguous buffer."""
+    lib = _lib.load()
+    _lib.require_cuda(packed, relpack, h0, h_out, q)
+    N = h0.shape[0]
+    eg_u, eg_a, eg_eps = explore if explore is not None else (None, None, None)
+    with _timed("agent_act_rel", (1, N, dims.ints(), (F_gt, cap_gt, F_ubs, cap_ubs, heads))):
+        _lib.check(lib.ubs_agent_act_rel_fwd(dims.H, dims.M, dims.K, dims.A, dims.U, dims.flags, _lib.ptr(packed),
+                                             _lib.ptr(relpack), x_gt_ptr, ip_seen_ptr, F_gt, cap_gt, x_ubs_ptr, ip_near_ptr,
+                                             F_ubs, cap_ubs, x_agent_ptr, F_d, heads, int(gat_flags), _lib.ptr(h0),
+                                             _lib.ptr(mask), _lib.ptr(h_out), _lib.ptr(q), _lib.ptr(acts), _lib.ptr(eg_u),
+                                             _lib.ptr(eg_a), _lib.ptr(eg_eps), N, _lib.stream()), "ubs_agent_act_rel_fwd")
+    return q
+
+
 class AgentSequence(th.autograd.Function):
     """Whole-sequence forward / backward of the recurrent part of the agent.
 

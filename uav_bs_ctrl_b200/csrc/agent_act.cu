@@ -64,7 +64,7 @@ __device__ __forceinline__ void bulk_copy(float* dst, const float* src, uint32_t
 // Tables of one relation (ubs_gatv2_rel_pack): wA[H] = W_src row (zero padded to 4), wR[H] = {W_res[0], W_res[1],
 // b_res, b_src}, wD[H] = {W_dst[0], W_dst[1], b_src + b_dst, (1-s)/2 attn}, hP[heads][8] = (1+s)/2 sum_d attn *
 // {W_src[0..3] | W_dst[0..1], b_src + b_dst, 0}: the same constants gatv2_fwd_kernel derives in its prologue.
-__host__ __device__ inline int rel_table_floats(int H, int heads) { return 12 * H + 8 * heads; }
+__host__ __device__ inline int rel_table_floats(int H, int heads) { return 12 * (H + heads) + 8 * heads; }   // one pad float4 per head
 
 struct RelSmem { int tabs, xs[2], cbuf, ips, xd, total; };     // float offsets inside the staging region
 __host__ __device__ inline RelSmem rel_smem(const StepDims& d, const RelIn& r) {
@@ -74,7 +74,7 @@ __host__ __device__ inline RelSmem rel_smem(const StepDims& d, const RelIn& r) {
     s.tabs = take(2 * rel_table_floats(d.H, r.heads));
     s.xs[0] = take(R * r.cap[0] * r.FS[0] + 4);
     s.xs[1] = take(R * r.cap[1] * r.FS[1] + 4);
-    s.cbuf = take((NT / 32) * 2 * d.H);
+    s.cbuf = take((NT / 32) * 2 * (d.H + r.heads));
     s.ips = take(2 * (R + 1));
     s.xd = take(2 * R);
     s.total = o;
@@ -96,109 +96,103 @@ __device__ __forceinline__ void lds_row(const float* p, float (&x)[FS]) {
 }
 
 // One warp, one destination: GATv2 over the source rows xs[beg .. end) (shared memory), result -> out[ch * RP].
-// Same arithmetic as gatv2_fwd_kernel (GS = 32 lanes per destination, two edges per lane per pass).
+// Same arithmetic as gatv2_fwd_kernel.  Heads are independent (own softmax, own output channels), so the warp is cut
+// into HEADS groups of LPH = 32 / HEADS lanes: a group owns one head and walks the edges two per lane per pass
+// (80 edges = 5 full passes of an 8-lane group; no idle lanes at the BASELINE degree).  The tables are padded by one
+// float4 per head so that the groups' weight reads fall into different banks.
 template <int FS, int HEADS>
 __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, const float* tab, int D, float xv0, float xv1,
                                          int flags, float2* cbuf, float* out) {
-    constexpr int HPW = HEADS >= 2 ? 2 : 1;        // heads per pass over the edges (register budget of a 512-thread CTA)
-    const int H = HEADS * D, lane = threadIdx.x & 31;
+    constexpr int LPH = 32 / HEADS;
+    const int H = HEADS * D, Hp = H + HEADS, Dp = D + 1, lane = threadIdx.x & 31;
+    const int k = lane / LPH, li = lane % LPH;
     const float4* wA = reinterpret_cast<const float4*>(tab);
-    const float4* wR = wA + H;
-    const float4* wD = wR + H;
-    const float* hP = reinterpret_cast<const float*>(wD + H);
+    const float4* wR = wA + Hp;
+    const float4* wD = wR + Hp;
+    const float* hP = reinterpret_cast<const float*>(wD + Hp);
     const bool relu = flags & UBS_GAT_RELU, has_res = flags & UBS_GAT_RESIDUAL;
     for (int ch = lane; ch < H; ch += 32) {
-        const float4 w = wD[ch];
-        cbuf[ch] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
+        const int p = ch + ch / D;
+        const float4 w = wD[p];
+        cbuf[p] = make_float2(fmaf(w.y, xv1, fmaf(w.x, xv0, w.z)), w.w);
     }
     __syncwarp();
-    for (int k0 = 0; k0 < HEADS; k0 += HPW) {
-        float lin[HPW], m[HPW], l[HPW], acc[HPW][FS];
+    const float4* wk = wA + k * Dp;
+    const float2* ck = cbuf + k * Dp;
+    const float4 pk = *reinterpret_cast<const float4*>(hP + k * 8);
+    const float lin = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
+    float m = -CUDART_INF_F, l = 0.f, acc[FS];
 #pragma unroll
-        for (int k = 0; k < HPW; ++k) {
-            lin[k] = fmaf(hP[(k0 + k) * 8 + 5], xv1, fmaf(hP[(k0 + k) * 8 + 4], xv0, hP[(k0 + k) * 8 + 6]));
-            m[k] = -CUDART_INF_F; l[k] = 0.f;
+    for (int f = 0; f < FS; ++f) acc[f] = 0.f;
+    for (int e = beg + li; e < end; e += 2 * LPH) {
+        float x[2][FS];
+        bool ok[2];
 #pragma unroll
-            for (int f = 0; f < FS; ++f) acc[k][f] = 0.f;
+        for (int j = 0; j < 2; ++j) {
+            const int ej = e + j * LPH;
+            ok[j] = ej < end;
+            if (ok[j]) lds_row<FS>(xs + ej * FS, x[j]);
+            else {
+#pragma unroll
+                for (int f = 0; f < FS; ++f) x[j][f] = 0.f;
+            }
         }
-        for (int e = beg + lane; e < end; e += 64) {
-            float x[2][FS];
-            bool ok[2];
+        float sc2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            sc2[j] = fmaf(pk.x, x[j][0], lin);
+            if constexpr (FS > 1) sc2[j] = fmaf(pk.y, x[j][1], sc2[j]);
+            if constexpr (FS > 2) sc2[j] = fmaf(pk.z, x[j][2], sc2[j]);
+            if constexpr (FS > 3) sc2[j] = fmaf(pk.w, x[j][3], sc2[j]);
+        }
+#pragma unroll 8
+        for (int dd = 0; dd < D; ++dd) {
+            const float4 w = wk[dd];
+            const float2 c = ck[dd];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int ej = e + j * 32;
-                ok[j] = ej < end;
-                if (ok[j]) lds_row<FS>(xs + ej * FS, x[j]);
-                else {
-#pragma unroll
-                    for (int f = 0; f < FS; ++f) x[j][f] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < HPW; ++k) {
-                const float4* wk = wA + (k0 + k) * D;
-                const float2* ck = cbuf + (k0 + k) * D;
-                const float4 pk = *reinterpret_cast<const float4*>(hP + (k0 + k) * 8);
-                float sc2[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    sc2[j] = fmaf(pk.x, x[j][0], lin[k]);
-                    if constexpr (FS > 1) sc2[j] = fmaf(pk.y, x[j][1], sc2[j]);
-                    if constexpr (FS > 2) sc2[j] = fmaf(pk.z, x[j][2], sc2[j]);
-                    if constexpr (FS > 3) sc2[j] = fmaf(pk.w, x[j][3], sc2[j]);
-                }
-#pragma unroll 8
-                for (int dd = 0; dd < D; ++dd) {
-                    const float4 w = wk[dd];
-                    const float2 c = ck[dd];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float z = c.x;
-                        z = fmaf(w.x, x[j][0], z);
-                        if constexpr (FS > 1) z = fmaf(w.y, x[j][1], z);
-                        if constexpr (FS > 2) z = fmaf(w.z, x[j][2], z);
-                        if constexpr (FS > 3) z = fmaf(w.w, x[j][3], z);
-                        sc2[j] = fmaf(c.y, fabsf(z), sc2[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (ok[j]) {
-                        const float mn = fmaxf(m[k], sc2[j]);
-                        const float sc = __expf(m[k] - mn);
-                        const float p = __expf(sc2[j] - mn);
-                        l[k] = fmaf(l[k], sc, p);
-#pragma unroll
-                        for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[j][f]);
-                        m[k] = mn;
-                    }
-                }
+                float z = c.x;
+                z = fmaf(w.x, x[j][0], z);
+                if constexpr (FS > 1) z = fmaf(w.y, x[j][1], z);
+                if constexpr (FS > 2) z = fmaf(w.z, x[j][2], z);
+                if constexpr (FS > 3) z = fmaf(w.w, x[j][3], z);
+                sc2[j] = fmaf(c.y, fabsf(z), sc2[j]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < HPW; ++k) {
-            const float Mx = warp_max(m[k]);
-            const float sc = (m[k] == -CUDART_INF_F) ? 0.f : __expf(m[k] - Mx);
-            l[k] = warp_sum(l[k] * sc);
+        for (int j = 0; j < 2; ++j) {
+            if (ok[j]) {
+                const float mn = fmaxf(m, sc2[j]);
+                const float sc = __expf(m - mn);
+                const float p = __expf(sc2[j] - mn);
+                l = fmaf(l, sc, p);
 #pragma unroll
-            for (int f = 0; f < FS; ++f) acc[k][f] = warp_sum(acc[k][f] * sc);
-            const float inv = l[k] > 0.f ? 1.0f / l[k] : 0.f;
-            for (int dd = lane; dd < D; dd += 32) {
-                const int ch = (k0 + k) * D + dd;
-                const float4 w = wA[ch];
-                const float4 r = wR[ch];
-                float o = 0.f;
-                if (l[k] > 0.f) {
-                    float t = w.x * acc[k][0];
-                    if constexpr (FS > 1) t = fmaf(w.y, acc[k][1], t);
-                    if constexpr (FS > 2) t = fmaf(w.z, acc[k][2], t);
-                    if constexpr (FS > 3) t = fmaf(w.w, acc[k][3], t);
-                    o = fmaf(t, inv, r.w);
-                }
-                if (has_res) o += fmaf(r.y, xv1, fmaf(r.x, xv0, r.z));
-                if (relu) o = fmaxf(o, 0.f);
-                out[ch * RP] = o;
+                for (int f = 0; f < FS; ++f) acc[f] = fmaf(acc[f], sc, p * x[j][f]);
+                m = mn;
             }
+        }
+    }
+    {
+        const float Mx = group_max<LPH>(m);
+        const float sc = (m == -CUDART_INF_F) ? 0.f : __expf(m - Mx);
+        l = group_sum<LPH>(l * sc);
+#pragma unroll
+        for (int f = 0; f < FS; ++f) acc[f] = group_sum<LPH>(acc[f] * sc);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        for (int dd = li; dd < D; dd += LPH) {
+            const float4 w = wk[dd];
+            const float4 r = wR[k * Dp + dd];
+            float o = 0.f;
+            if (l > 0.f) {
+                float t = w.x * acc[0];
+                if constexpr (FS > 1) t = fmaf(w.y, acc[1], t);
+                if constexpr (FS > 2) t = fmaf(w.z, acc[2], t);
+                if constexpr (FS > 3) t = fmaf(w.w, acc[3], t);
+                o = fmaf(t, inv, r.w);
+            }
+            if (has_res) o += fmaf(r.y, xv1, fmaf(r.x, xv0, r.z));
+            if (relu) o = fmaxf(o, 0.f);
+            out[(k * D + dd) * RP] = o;
         }
     }
     __syncwarp();
@@ -425,7 +419,7 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
             mbar_wait(bars + 2, 0);
             {
                 const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;      // warp = destination row of the tile
-                float2* cb = reinterpret_cast<float2*>(stage + rs.cbuf) + r * H;
+                float2* cb = reinterpret_cast<float2*>(stage + rs.cbuf) + r * (H + rl.heads);
                 const int D = H / rl.heads;
 #pragma unroll
                 for (int rel = 0; rel < 2; ++rel) {
@@ -594,15 +588,18 @@ struct RelPackArgs {
 };
 
 __global__ void __launch_bounds__(256) gatv2_rel_pack_kernel(const RelPackArgs a) {
-    const int H = a.heads * a.D;
+    const int H = a.heads * a.D, Hp = H + a.heads;          // padded: channel ch lives at index ch + ch / D
     float4* wA = reinterpret_cast<float4*>(a.out);
-    float4* wR = wA + H;
-    float4* wD = wR + H;
-    float* hP = reinterpret_cast<float*>(wD + H);
+    float4* wR = wA + Hp;
+    float4* wD = wR + Hp;
+    float* hP = reinterpret_cast<float*>(wD + Hp);
+    for (int i = threadIdx.x; i < 3 * Hp; i += 256) wA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     for (int ch = threadIdx.x; ch < H; ch += 256) {
+        const int p = ch + ch / a.D;
         float w[4] = {0.f, 0.f, 0.f, 0.f};
         for (int f = 0; f < a.FS; ++f) w[f] = a.W_src[ch * a.FS + f];
-        wA[ch] = make_float4(w[0], w[1], w[2], w[3]);
+        wA[p] = make_float4(w[0], w[1], w[2], w[3]);
         const float bs = a.b_src ? a.b_src[ch] : 0.f;
         const float bd = a.b_dst ? a.b_dst[ch] : 0.f;
         float r0 = 0.f, r1 = 0.f, rb = 0.f;
@@ -611,22 +608,22 @@ __global__ void __launch_bounds__(256) gatv2_rel_pack_kernel(const RelPackArgs a
             r1 = a.FD > 1 ? a.W_res[ch * a.FD + 1] : 0.f;
             rb = a.b_res ? a.b_res[ch] : 0.f;
         }
-        wR[ch] = make_float4(r0, r1, rb, bs);
-        wD[ch] = make_float4(a.W_dst[ch * a.FD], a.FD > 1 ? a.W_dst[ch * a.FD + 1] : 0.f, bs + bd,
-                             0.5f * (1.0f - a.slope) * a.attn[ch]);
+        wR[p] = make_float4(r0, r1, rb, bs);
+        wD[p] = make_float4(a.W_dst[ch * a.FD], a.FD > 1 ? a.W_dst[ch * a.FD + 1] : 0.f, bs + bd,
+                            0.5f * (1.0f - a.slope) * a.attn[ch]);
     }
     __syncthreads();
     if (threadIdx.x < a.heads * 8) {
         const int k = threadIdx.x / 8, j = threadIdx.x % 8;
         float acc = 0.f;
         for (int d0 = 0; d0 < a.D; ++d0) {
-            const int ch = k * a.D + d0;
+            const int ch = k * a.D + d0, p = ch + k;
             const float at = a.attn[ch];
             float w = 0.f;
-            if (j < 4) w = j == 0 ? wA[ch].x : j == 1 ? wA[ch].y : j == 2 ? wA[ch].z : wA[ch].w;
-            else if (j == 4) w = wD[ch].x;
-            else if (j == 5) w = wD[ch].y;
-            else if (j == 6) w = wD[ch].z;
+            if (j < 4) w = j == 0 ? wA[p].x : j == 1 ? wA[p].y : j == 2 ? wA[p].z : wA[p].w;
+            else if (j == 4) w = wD[p].x;
+            else if (j == 5) w = wD[p].y;
+            else if (j == 6) w = wD[p].z;
             acc = fmaf(at, w, acc);
         }
         hP[threadIdx.x] = 0.5f * (1.0f + a.slope) * acc;

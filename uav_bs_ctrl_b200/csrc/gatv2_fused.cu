@@ -452,6 +452,265 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
     for (int i = threadIdx.x; i < P; i += 128) a.partial[(size_t)blockIdx.x * P + i] = red[i];
 }
 
+// ---- backward for leaf observations (grad_x_src == NULL: every env config), two passes per chunk of 32 edges ----------
+// The kernel above lets every lane walk every edge of its destination: the per-edge scalar work (score reduction by
+// shuffles, expf, the softmax gradient) is repeated by all lanes of a head and sits on the dependent path of the
+// channel loop.  Here a chunk of 32 edges is processed twice:
+//   pass 1, lanes own EDGES (like the forward): score of every head with the weights broadcast from shared memory,
+//           alpha = exp(s - max) / sum, ds = alpha (<g', el> - <g', ft>) -> shared memory; sum_e alpha x_e in registers;
+//   pass 2, lanes own CHANNELS: only the parameter-gradient FMAs — z recomputed from the 16-byte source row,
+//           g_attn += ds y,  t = ds lrelu'(z),  sum_e t x_e,  sum_e t — no shuffles, no expf, no per-head redundancy.
+// Same per-CTA partials + fixed-order reduction as above (deterministic).
+template <int FS, int CPL, int HEADS>
+__global__ void __launch_bounds__(128) gatv2_bwd2_kernel(const GatArgs a) {
+    constexpr int H = 32 * CPL, D = H / HEADS, LPH = 32 / HEADS;
+    static_assert(D % CPL == 0, "a lane's channels must stay inside one head");
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int head = (lane * CPL) / D;
+    const int FD = a.F_d;
+    const bool relu = a.flags & UBS_GAT_RELU, has_res = a.flags & UBS_GAT_RESIDUAL;
+    const float slope = a.slope;
+    __shared__ float4 wA[H];                   // W_src rows (zero padded to 4)
+    __shared__ float2 cb[4][H];                // per warp: {W_dst x_v + b_src + b_dst, (1-s)/2 attn} per channel
+    __shared__ float hP[HEADS * 8];            // (1+s)/2 sum_d attn {W_src[0..3] | W_dst[0..1], b_src + b_dst}
+    __shared__ float4 xs[4][32];               // source rows of the chunk
+    __shared__ float dsS[4][HEADS][33];        // softmax-gradient of the chunk's (edge, head) scores (+1: bank skew)
+    __shared__ float4 hc[4][HEADS][2];         // per (warp, head): {<g',ft>, <g',b_src>, <g',W_src[:,0..1]>}, {.., [:,2..3], max, 1/sum}
+    __shared__ float red[H * (4 + 2 * 2 + 4)];
+
+    float ws[CPL][FS], wd[CPL][2], wr[CPL][2], bsum[CPL], bs[CPL], brr[CPL], at[CPL];
+    float g_ws[CPL][FS], g_wd[CPL][2], g_wr[CPL][2], g_bsd[CPL], g_bsm[CPL], g_br[CPL], g_at[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int ch = lane * CPL + j;
+#pragma unroll
+        for (int f = 0; f < FS; ++f) { ws[j][f] = a.W_src[ch * FS + f]; g_ws[j][f] = 0.f; }
+        wd[j][0] = a.W_dst[ch * FD]; wd[j][1] = FD > 1 ? a.W_dst[ch * FD + 1] : 0.f;
+        wr[j][0] = has_res ? a.W_res[ch * FD] : 0.f;
+        wr[j][1] = (has_res && FD > 1) ? a.W_res[ch * FD + 1] : 0.f;
+        brr[j] = (has_res && a.b_res) ? a.b_res[ch] : 0.f;
+        bs[j] = a.b_src ? a.b_src[ch] : 0.f;
+        bsum[j] = bs[j] + (a.b_dst ? a.b_dst[ch] : 0.f);
+        at[j] = a.attn[ch];
+        g_wd[j][0] = g_wd[j][1] = g_wr[j][0] = g_wr[j][1] = 0.f;
+        g_bsd[j] = g_bsm[j] = g_br[j] = g_at[j] = 0.f;
+    }
+    for (int ch = threadIdx.x; ch < H; ch += 128) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < FS; ++f) w[f] = a.W_src[ch * FS + f];
+        wA[ch] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+    if (threadIdx.x < HEADS * 8) {
+        const int k = threadIdx.x / 8, j = threadIdx.x % 8;
+        float acc = 0.f;
+        for (int d0 = 0; d0 < D; ++d0) {
+            const int ch = k * D + d0;
+            float w = 0.f;
+            if (j < 4) w = j == 0 ? wA[ch].x : j == 1 ? wA[ch].y : j == 2 ? wA[ch].z : wA[ch].w;
+            else if (j == 4) w = a.W_dst[ch * FD];
+            else if (j == 5) w = FD > 1 ? a.W_dst[ch * FD + 1] : 0.f;
+            else if (j == 6) w = (a.b_src ? a.b_src[ch] : 0.f) + (a.b_dst ? a.b_dst[ch] : 0.f);
+            acc = fmaf(a.attn[ch], w, acc);
+        }
+        hP[threadIdx.x] = 0.5f * (1.0f + slope) * acc;
+    }
+    __syncthreads();
+
+    const int total_warps = gridDim.x * 4;
+    for (int v = blockIdx.x * 4 + warp; v < a.n_dst; v += total_warps) {
+        const int seg = v / a.n_dst_seg, vl = v - seg * a.n_dst_seg;
+        const float* xsrc = a.x_src + seg * a.st_xsrc;
+        const int* sidx = a.src_idx ? a.src_idx + seg * a.st_sidx : nullptr;
+        const int* ip = a.indptr + seg * a.st_ip;
+        const float* xd = a.x_dst + seg * a.st_xdst + (size_t)vl * FD;
+        const int beg = __ldg(ip + vl), end = __ldg(ip + vl + 1);
+        const float xv0 = __ldg(xd);
+        const float xv1 = FD > 1 ? __ldg(xd + 1) : 0.f;
+        float gp[CPL], ft[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int chj = lane * CPL + j;
+            const float go = __ldg(a.grad_out + (size_t)v * a.ld_gout + chj), oo = __ldg(a.out_in + (size_t)v * a.ld_out + chj);
+            gp[j] = (relu && !(oo > 0.f)) ? 0.f : go;
+            const float res = has_res ? fmaf(wr[j][1], xv1, fmaf(wr[j][0], xv0, brr[j])) : 0.f;
+            ft[j] = oo - res;                                   // only used where gp != 0
+            g_wr[j][0] = fmaf(gp[j], xv0, g_wr[j][0]);
+            g_wr[j][1] = fmaf(gp[j], xv1, g_wr[j][1]);
+            g_br[j] += gp[j];
+        }
+        float sdz[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) sdz[j] = 0.f;
+        if (end > beg) {                                        // warp-uniform
+            float dotp = 0.f, qk = 0.f, pk[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                dotp = fmaf(gp[j], ft[j], dotp);
+                qk = fmaf(gp[j], bs[j], qk);
+#pragma unroll
+                for (int f = 0; f < FS; ++f) pk[f] = fmaf(gp[j], ws[j][f], pk[f]);
+            }
+            dotp = group_sum<LPH>(dotp);
+            qk = group_sum<LPH>(qk);
+#pragma unroll
+            for (int f = 0; f < FS; ++f) pk[f] = group_sum<LPH>(pk[f]);
+            float c[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                c[j] = fmaf(wd[j][1], xv1, fmaf(wd[j][0], xv0, bsum[j]));
+                cb[warp][lane * CPL + j] = make_float2(c[j], 0.5f * (1.0f - slope) * at[j]);
+            }
+            if (lane % LPH == 0) {
+                hc[warp][head][0] = make_float4(dotp, qk, pk[0], pk[1]);
+                hc[warp][head][1] = make_float4(pk[2], pk[3], __ldg(a.smax_in + (size_t)v * HEADS + head),
+                                                1.0f / __ldg(a.ssum_in + (size_t)v * HEADS + head));
+            }
+            __syncwarp();
+            float abar[HEADS][FS], tws[CPL][FS], st[CPL];
+#pragma unroll
+            for (int k = 0; k < HEADS; ++k)
+#pragma unroll
+                for (int f = 0; f < FS; ++f) abar[k][f] = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                st[j] = 0.f;
+#pragma unroll
+                for (int f = 0; f < FS; ++f) tws[j][f] = 0.f;
+            }
+            for (int e0 = beg; e0 < end; e0 += 32) {
+                const int cnt = min(32, end - e0);
+                // ---- pass 1: lane = edge
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (lane < cnt) {
+                    const size_t u = sidx ? (size_t)__ldg(sidx + e0 + lane) : (size_t)(e0 + lane);
+                    float xr[FS];
+                    load_row<FS>(xsrc, u, xr);
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) x[f] = xr[f];
+                }
+                xs[warp][lane] = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                for (int k = 0; k < HEADS; ++k) {
+                    const float4 h0 = hc[warp][k][0], h1 = hc[warp][k][1];
+                    const float4 pl = *reinterpret_cast<const float4*>(hP + k * 8);
+                    float s = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
+                    s = fmaf(pl.x, x[0], s);
+                    if constexpr (FS > 1) s = fmaf(pl.y, x[1], s);
+                    if constexpr (FS > 2) s = fmaf(pl.z, x[2], s);
+                    if constexpr (FS > 3) s = fmaf(pl.w, x[3], s);
+                    const float4* wk = wA + k * D;
+                    const float2* ck = cb[warp] + k * D;
+#pragma unroll 8
+                    for (int d = 0; d < D; ++d) {
+                        const float4 w = wk[d];
+                        const float2 cc = ck[d];
+                        float z = cc.x;
+                        z = fmaf(w.x, x[0], z);
+                        if constexpr (FS > 1) z = fmaf(w.y, x[1], z);
+                        if constexpr (FS > 2) z = fmaf(w.z, x[2], z);
+                        if constexpr (FS > 3) z = fmaf(w.w, x[3], z);
+                        s = fmaf(cc.y, fabsf(z), s);
+                    }
+                    const float alpha = lane < cnt ? __expf(s - h1.z) * h1.w : 0.f;
+                    float da = h0.y;
+                    da = fmaf(h0.z, x[0], da);
+                    if constexpr (FS > 1) da = fmaf(h0.w, x[1], da);
+                    if constexpr (FS > 2) da = fmaf(h1.x, x[2], da);
+                    if constexpr (FS > 3) da = fmaf(h1.y, x[3], da);
+                    dsS[warp][k][lane] = alpha * (da - h0.x);
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) abar[k][f] = fmaf(alpha, x[f], abar[k][f]);
+                }
+                __syncwarp();
+                // ---- pass 2: lane = CPL channels
+                const float* dsh = dsS[warp][head];
+#pragma unroll 2
+                for (int i = 0; i < cnt; ++i) {
+                    const float4 t4 = xs[warp][i];
+                    const float xx[4] = {t4.x, t4.y, t4.z, t4.w};
+                    const float dsv = dsh[i];
+                    const float dsl = dsv * slope;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        float z = c[j];
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) z = fmaf(ws[j][f], xx[f], z);
+                        const float y = fmaxf(z, slope * z);
+                        g_at[j] = fmaf(dsv, y, g_at[j]);
+                        const float t = z > 0.f ? dsv : dsl;
+#pragma unroll
+                        for (int f = 0; f < FS; ++f) tws[j][f] = fmaf(t, xx[f], tws[j][f]);
+                        st[j] += t;
+                    }
+                }
+                __syncwarp();
+            }
+            // sum_e alpha x_e of this lane's head
+            float ab[FS];
+#pragma unroll
+            for (int f = 0; f < FS; ++f) ab[f] = 0.f;
+#pragma unroll
+            for (int k = 0; k < HEADS; ++k)
+#pragma unroll
+                for (int f = 0; f < FS; ++f) {
+                    const float tot = warp_sum(abar[k][f]);
+                    if (k == head) ab[f] = tot;
+                }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                sdz[j] = at[j] * st[j];
+#pragma unroll
+                for (int f = 0; f < FS; ++f) g_ws[j][f] += fmaf(at[j], tws[j][f], gp[j] * ab[f]);   // score path + message path
+                g_bsm[j] += gp[j];                                                                 // sum_e alpha = 1
+                g_wd[j][0] = fmaf(sdz[j], xv0, g_wd[j][0]);
+                g_wd[j][1] = fmaf(sdz[j], xv1, g_wd[j][1]);
+                g_bsd[j] += sdz[j];
+            }
+        }
+        if (a.grad_x_dst != nullptr) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                t0 += sdz[j] * wd[j][0] + gp[j] * wr[j][0];
+                t1 += sdz[j] * wd[j][1] + gp[j] * wr[j][1];
+            }
+            t0 = warp_sum(t0); t1 = warp_sum(t1);
+            if (lane == 0) {
+                float* gd = a.grad_x_dst + seg * a.st_xdst + (size_t)vl * FD;
+                gd[0] = t0;
+                if (FD > 1) gd[1] = t1;
+            }
+        }
+    }
+
+    // ---- CTA reduction in a fixed warp order, then one partial row per CTA
+    const int oWs = 0, obs = H * FS, oWd = obs + H, obd = oWd + H * FD, oat = obd + H, oWr = oat + H,
+              obr = oWr + H * FD, P = obr + H;
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int ch = lane * CPL + j;
+                auto put = [&](int idx, float val) { red[idx] = (w == 0) ? val : red[idx] + val; };
+#pragma unroll
+                for (int f = 0; f < FS; ++f) put(oWs + ch * FS + f, g_ws[j][f]);
+                put(obs + ch, g_bsd[j] + g_bsm[j]);
+                put(oWd + ch * FD, g_wd[j][0]);
+                if (FD > 1) put(oWd + ch * FD + 1, g_wd[j][1]);
+                put(obd + ch, g_bsd[j]);
+                put(oat + ch, g_at[j]);
+                put(oWr + ch * FD, g_wr[j][0]);
+                if (FD > 1) put(oWr + ch * FD + 1, g_wr[j][1]);
+                put(obr + ch, g_br[j]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < P; i += 128) a.partial[(size_t)blockIdx.x * P + i] = red[i];
+}
+
 // out[i] = sum_p partial[p*P + i], fixed order: 8 slices of parts per column, combined in slice order.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int P,
                                                               float* __restrict__ out) {
@@ -519,6 +778,16 @@ static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
 template <int FS, int HEADS>
 static int launch_bwd(const GatArgs& a, int H, cudaStream_t st) {
     const int grid = bwd_grid(a.n_dst);
+    static const bool two_pass = [] { const char* e = getenv("UBS_GAT_BWD2"); return !(e && e[0] == '0'); }();
+    if (a.grad_x_src == nullptr && two_pass) {             // observations are leaves: the two-pass kernel
+        switch (H / 32) {
+            case 1: gatv2_bwd2_kernel<FS, 1, HEADS><<<grid, 128, 0, st>>>(a); break;
+            case 2: gatv2_bwd2_kernel<FS, 2, HEADS><<<grid, 128, 0, st>>>(a); break;
+            case 4: gatv2_bwd2_kernel<FS, 4, HEADS><<<grid, 128, 0, st>>>(a); break;
+            default: set_error("ubs_gatv2_bwd: H=%d unsupported (32, 64, 128)", H); return 2;
+        }
+        return check_launch("ubs_gatv2_bwd");
+    }
     switch (H / 32) {
         case 1: gatv2_bwd_kernel<FS, 1, HEADS><<<grid, 128, 0, st>>>(a); break;
         case 2: gatv2_bwd_kernel<FS, 2, HEADS><<<grid, 128, 0, st>>>(a); break;

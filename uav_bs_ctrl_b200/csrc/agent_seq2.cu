@@ -13,6 +13,7 @@
 // A CTA owns a tile of <= 16 agent rows (whole envs; envs never exchange data) for all timesteps.
 #include "common.cuh"
 #include "../../include/ubs_gnn.h"
+#include <stdlib.h>
 
 namespace ubs {
 namespace seq2 {
@@ -364,6 +365,300 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
     if (a.d_h0 != nullptr) store_tile(a.d_h0, row0, n_valid, H, H, sDH);
 }
 
+// ================================================================================================ tensor-core path
+// The same window kernels with every dense product on the tensor cores.  A CTA still owns 16 agent rows — exactly the M
+// of one mma.sync.m16n8k8 tile — so the per-step products h W_hh^T (16 x H x 3H), h W_vsq_h^T (16 x H x Vp) and
+// c W_ih_c^T (16 x M x 3H) become 8-column warp tiles whose accumulators stay in registers; fp32 accuracy comes from
+// the 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulate: ~2^-21),
+// done on the fly in registers because hi / lo copies of the resident weights (2 x 123 KB) would not fit one SM.
+//   * warp w < H/8 ("gate warp") owns the 8 channels [8w, 8w+8) of all three gates: its gh and gi accumulators and the
+//     hidden state of its (row, channel) elements never leave registers — the GRU gates run on the accumulator
+//     fragments directly, h' goes to shared memory only as the next step's A operand;
+//   * warps 8..15 ("comm warps") produce vsq = pv + h W_vsq_h^T, run the block attention and hand c to the gate warps,
+//     concurrently with the gate warps' gh product (both only need h);
+//   * weights sit K-major with the row stride padded to 8 (mod 32) floats and activations row-major with stride
+//     4 (mod 32): every fragment load is bank-conflict free.
+// tcgen05 is the wrong tool here: its smallest tile (M = 64) would need the transposed product with both operands
+// pre-split in shared memory, and every dependent layer would pay a TMEM -> register -> shared-memory round trip; the
+// chain of three dependent 16-row products per timestep is latency-, not throughput-bound.
+namespace mma {
+
+constexpr int NW = 16, NTM = NW * 32, NGATE = 8;
+
+__device__ __forceinline__ void split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;                       // explicit truncation: the MMA must see exactly hi
+    lo = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
+}
+__device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__host__ __device__ inline int pad8(int n) { return n + ((8 - n % 32) + 32) % 32; }     // == 8 (mod 32)
+__host__ __device__ inline int pad4(int n) { return n + ((4 - n % 32) + 32) % 32; }     // == 4 (mod 32)
+
+// acc[j] (+)= A[16 x Kd] (shared, row-major, stride lda) . W[Kd x 8] at columns n0[j] (shared, K-major, stride ldw)
+// for NT column tiles of one warp; main / corr keep the hi.hi and the two cross terms apart.
+template <int NT>
+__device__ __forceinline__ void warp_gemm(const float* A, int lda, int Kd, const float* W, int ldw, const int (&n0)[NT],
+                                          int ntiles, float (&main_)[NT][4], float (&corr)[NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const float* a0p = A + g * lda + c;
+    const float* a1p = a0p + 8 * lda;
+    for (int k0 = 0; k0 < Kd; k0 += 8) {
+        uint32_t ah[4], al[4];
+        split(a0p[k0], ah[0], al[0]);
+        split(a1p[k0], ah[1], al[1]);
+        split(a0p[k0 + 4], ah[2], al[2]);
+        split(a1p[k0 + 4], ah[3], al[3]);
+        const float* wp = W + (k0 + c) * ldw + g;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (j < ntiles) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split(wp[n0[j]], bh0, bl0);
+                split(wp[n0[j] + 4 * ldw], bh1, bl1);
+                mma8(corr[j], al, bh0, bh1);
+                mma8(corr[j], ah, bl0, bl1);
+                mma8(main_[j], ah, bh0, bh1);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct Smem { int wVH, wIC, wHH, bHH, sH, sC, sVSQ, sAl, total; int ldV, ld3, ldh, ldc, ldv; };
+__host__ __device__ inline Smem fwd_layout(const Dims& d) {
+    Smem s{};
+    const int H = d.H, H3 = 3 * H, Vp = d.Vp();
+    s.ldV = pad8(Vp); s.ld3 = pad8(H3); s.ldh = pad4(H); s.ldc = pad4(d.M > 0 ? d.M : 4); s.ldv = pad4(Vp > 0 ? Vp : 4);
+    int o = 0;
+    auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
+    s.wVH = take(d.tarmac() ? H * s.ldV : 0);
+    s.wIC = take(d.tarmac() ? d.M * s.ld3 : 0);
+    s.wHH = take(H * s.ld3);
+    s.bHH = take(H3);
+    s.sH = take(R * s.ldh);
+    s.sC = take(d.tarmac() ? R * s.ldc : 0);
+    s.sVSQ = take(d.tarmac() ? R * s.ldv : 0);
+    s.sAl = take(d.tarmac() ? R * d.U : 0);
+    s.total = o;
+    return s;
+}
+__host__ __device__ inline bool fwd_supported(const Dims& d) {
+    if (!(d.H == 32 || d.H == 64)) return false;
+    if (d.tarmac() && (d.M % 8 || d.M < 8 || d.Vp() % 8 || d.Vp() / 8 > 16)) return false;
+    return (size_t)fwd_layout(d).total * sizeof(float) <= 227 * 1024;
+}
+
+__device__ __forceinline__ void copy_padded(float* dst, int ld_dst, const float* __restrict__ src, int rows, int cols) {
+    const int c4 = cols >> 2;
+    for (int i = threadIdx.x; i < rows * c4; i += NTM) {
+        const int r = i / c4, q = i - r * c4;
+        *reinterpret_cast<float4*>(dst + r * ld_dst + 4 * q) = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + 4 * q));
+    }
+}
+
+__global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
+    extern __shared__ __align__(16) float sm[];
+    const Dims d = a.d;
+    const int H = d.H, H3 = 3 * H, M = d.M, K = d.K, U = d.U, Vp = d.Vp();
+    const bool tm = d.tarmac();
+    const Smem L = fwd_layout(d);
+    float* wVH = sm + L.wVH; float* wIC = sm + L.wIC; float* wHH = sm + L.wHH; float* bHH = sm + L.bHH;
+    float* sH = sm + L.sH; float* sC = sm + L.sC; float* sVSQ = sm + L.sVSQ; float* sAl = sm + L.sAl;
+    if (tm) { copy_padded(wVH, L.ldV, a.w0, H, Vp); copy_padded(wIC, L.ld3, a.w1, M, H3); }
+    copy_padded(wHH, L.ld3, a.w2, H, H3);
+    for (int i = threadIdx.x; i < H3; i += NTM) bHH[i] = __ldg(a.b_hh + i);
+
+    const int rpt = d.rows_per_tile();
+    const int64_t row0 = (int64_t)blockIdx.x * rpt;
+    const int n_valid = (int)min((int64_t)rpt, a.N - row0);
+    const int64_t n = a.N;
+    const bool training = a.sv_gate != nullptr;
+    const float scale = tm ? 1.0f / (float)K : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const bool gate_warp = warp < NGATE && warp < H / 8;
+    const bool comm_warp = warp >= NGATE;
+    const int cw = warp - NGATE, ct = threadIdx.x - NGATE * 32;           // comm warp / thread index
+    const int NCT = (NW - NGATE) * 32;
+    const int r0 = g, r1 = g + 8;                                          // fragment rows of this lane
+    const bool v0 = r0 < n_valid, v1 = r1 < n_valid;
+    const int chb = 8 * warp + 2 * c;                                      // gate warps: first of this lane's 2 channels
+
+    for (int i = threadIdx.x; i < R * L.ldh; i += NTM) {
+        const int r = i / L.ldh, f = i - r * L.ldh;
+        sH[i] = (r < n_valid && f < H) ? __ldg(a.h0 + (row0 + r) * H + f) : 0.f;
+    }
+    float hreg[4] = {0.f, 0.f, 0.f, 0.f};                                  // h[r0][chb], h[r0][chb+1], h[r1][chb], h[r1][chb+1]
+    if (gate_warp) {
+        if (v0) { hreg[0] = __ldg(a.h0 + (row0 + r0) * H + chb); hreg[1] = __ldg(a.h0 + (row0 + r0) * H + chb + 1); }
+        if (v1) { hreg[2] = __ldg(a.h0 + (row0 + r1) * H + chb); hreg[3] = __ldg(a.h0 + (row0 + r1) * H + chb + 1); }
+    }
+    const int vtiles = tm ? Vp / 8 : 0;
+    const int my_vt = comm_warp ? ((cw < vtiles) + (cw + 8 < vtiles)) : 0;
+    const int vn0[2] = {8 * cw, 8 * (cw + 8)};
+    float pvr[2][4];                                                       // comm warps: pv fragments of the coming step
+    auto load_pv = [&](int t) {
+        const float* pv = a.pv + (size_t)t * n * a.ld_pv;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            pvr[j][0] = pvr[j][1] = pvr[j][2] = pvr[j][3] = 0.f;
+            if (j < my_vt) {
+                const int col = vn0[j] + 2 * c;
+                if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r0) * a.ld_pv + col)); pvr[j][0] = t2.x; pvr[j][1] = t2.y; }
+                if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r1) * a.ld_pv + col)); pvr[j][2] = t2.x; pvr[j][3] = t2.y; }
+            }
+        }
+    };
+    if (comm_warp && tm) load_pv(0);
+    __syncthreads();
+
+    for (int t = 0; t < a.T; ++t) {
+        const float* pg = a.pg + (size_t)t * n * a.ld_pg;
+        float gh[3][4], gi[3][4];
+        if (gate_warp) {
+            // ---- gi initialisers (global, needed after phase A: the loads fly during the gh product)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int col = j * H + chb;
+                gi[j][0] = gi[j][1] = gi[j][2] = gi[j][3] = 0.f;
+                if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r0) * a.ld_pg + col)); gi[j][0] = t2.x; gi[j][1] = t2.y; }
+                if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r1) * a.ld_pg + col)); gi[j][2] = t2.x; gi[j][3] = t2.y; }
+            }
+            // ---- phase A: gh = h W_hh^T + b_hh
+            float corr[3][4];
+            const int n0[3] = {8 * warp, H + 8 * warp, 2 * H + 8 * warp};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float b0 = bHH[n0[j] + 2 * c], b1 = bHH[n0[j] + 2 * c + 1];
+                gh[j][0] = b0; gh[j][1] = b1; gh[j][2] = b0; gh[j][3] = b1;
+                corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
+            }
+            warp_gemm<3>(sH, L.ldh, H, wHH, L.ld3, n0, 3, gh, corr);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gh[j][q] += corr[j][q];
+        } else if (comm_warp && tm) {
+            // ---- phase A': vsq = pv + h W_vsq_h^T  ->  shared memory (+ saved for the backward)
+            float corr[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
+            warp_gemm<2>(sH, L.ldh, H, wVH, L.ldV, vn0, my_vt, pvr, corr);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j < my_vt) {
+                    const int col = vn0[j] + 2 * c;
+                    const float2 lo2 = make_float2(pvr[j][0] + corr[j][0], pvr[j][1] + corr[j][1]);
+                    const float2 hi2 = make_float2(pvr[j][2] + corr[j][2], pvr[j][3] + corr[j][3]);
+                    *reinterpret_cast<float2*>(sVSQ + r0 * L.ldv + col) = lo2;
+                    *reinterpret_cast<float2*>(sVSQ + r1 * L.ldv + col) = hi2;
+                    if (training) {
+                        float* sv = a.sv_vsq + (size_t)t * n * Vp;
+                        if (v0) *reinterpret_cast<float2*>(sv + (row0 + r0) * Vp + col) = lo2;
+                        if (v1) *reinterpret_cast<float2*>(sv + (row0 + r1) * Vp + col) = hi2;
+                    }
+                }
+            }
+            bar_sync(1, NCT);
+            // ---- block attention (TarMAC.forward: u_dot_v / key_size, edge_softmax, u_mul_e + sum)
+            const uint32_t* mk = a.mask + (size_t)t * n;
+            for (int p = ct; p < R * U; p += NCT) {
+                const int r = p / U, i = p - r * U;
+                float e = -CUDART_INF_F;
+                if (r < n_valid && ((__ldg(mk + row0 + r) >> i) & 1u)) {
+                    const float* sp = sVSQ + ((r / U) * U + i) * L.ldv + M;       // signature of the source
+                    const float* qp = sVSQ + r * L.ldv + M + K;                   // query of the destination
+                    float acc = 0.f;
+                    for (int kk = 0; kk < K; ++kk) acc = fmaf(sp[kk], qp[kk], acc);
+                    e = acc * scale;
+                }
+                sAl[r * U + i] = e;
+            }
+            bar_sync(1, NCT);
+            if (ct < R) {
+                const int r = ct;
+                float mx = -CUDART_INF_F;
+                for (int i = 0; i < U; ++i) mx = fmaxf(mx, sAl[r * U + i]);
+                float den = 0.f;
+                for (int i = 0; i < U; ++i) {
+                    const float e = sAl[r * U + i];
+                    const float pr = e == -CUDART_INF_F ? 0.f : expf(e - mx);
+                    sAl[r * U + i] = pr;
+                    den += pr;
+                }
+                const float inv = den > 0.f ? 1.0f / den : 0.f;
+                for (int i = 0; i < U; ++i) {
+                    const float al = sAl[r * U + i] * inv;
+                    sAl[r * U + i] = al;
+                    if (training && r < n_valid) a.sv_alpha[((size_t)t * n + row0 + r) * U + i] = al;
+                }
+            }
+            bar_sync(1, NCT);
+            for (int p = ct; p < R * M; p += NCT) {
+                const int r = p / M, m = p - r * M;
+                const int b0 = (r / U) * U;
+                float acc = 0.f;
+                if (r < n_valid)
+                    for (int i = 0; i < U; ++i) acc = fmaf(sAl[r * U + i], sVSQ[(b0 + i) * L.ldv + m], acc);
+                sC[r * L.ldc + m] = acc;
+                if (training && r < n_valid) a.sv_c[((size_t)t * n + row0 + r) * M + m] = acc;
+            }
+            if (t + 1 < a.T) load_pv(t + 1);
+        }
+        __syncthreads();                                    // c is ready; everybody has finished reading h
+        if (gate_warp) {
+            // ---- phase B: gi = pg + c W_ih_c^T, then the GRU gates on the accumulator fragments
+            if (tm) {
+                float corr[3][4];
+                const int n0[3] = {8 * warp, H + 8 * warp, 2 * H + 8 * warp};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
+                warp_gemm<3>(sC, L.ldc, M, wIC, L.ld3, n0, 3, gi, corr);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gi[j][q] += corr[j][q];
+            }
+            float hn[4], rr[4], zz[4], nn[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rr[q] = sigmoidf_(gi[0][q] + gh[0][q]);
+                zz[q] = sigmoidf_(gi[1][q] + gh[1][q]);
+                nn[q] = tanhf(fmaf(rr[q], gh[2][q], gi[2][q]));
+                hn[q] = fmaf(zz[q], hreg[q] - nn[q], nn[q]);
+                hreg[q] = hn[q];
+            }
+            *reinterpret_cast<float2*>(sH + r0 * L.ldh + chb) = make_float2(hn[0], hn[1]);
+            *reinterpret_cast<float2*>(sH + r1 * L.ldh + chb) = make_float2(hn[2], hn[3]);
+            float* hout = a.h_out + (size_t)t * n * H;
+            if (v0) *reinterpret_cast<float2*>(hout + (row0 + r0) * H + chb) = make_float2(hn[0], hn[1]);
+            if (v1) *reinterpret_cast<float2*>(hout + (row0 + r1) * H + chb) = make_float2(hn[2], hn[3]);
+            if (training) {
+                float* gt = a.sv_gate + (size_t)t * n * 4 * H;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 0 ? v0 : v1) {
+                        float* gp = gt + (row0 + (half == 0 ? r0 : r1)) * 4 * H + chb;
+                        const int q = 2 * half;
+                        *reinterpret_cast<float2*>(gp) = make_float2(rr[q], rr[q + 1]);
+                        *reinterpret_cast<float2*>(gp + H) = make_float2(zz[q], zz[q + 1]);
+                        *reinterpret_cast<float2*>(gp + 2 * H) = make_float2(nn[q], nn[q + 1]);
+                        *reinterpret_cast<float2*>(gp + 3 * H) = make_float2(gh[2][q], gh[2][q + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                    // h' is in shared memory for the next step
+    }
+}
+
+}  // namespace mma
+
 static size_t fwd_smem(const Dims& d) {
     const int H = d.H, H3 = 3 * H, Vp = d.Vp();
     size_t f = (size_t)H * H3 + H3 + (size_t)(H + 2 * H3) * RP + NT * 16;
@@ -413,6 +708,16 @@ extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags,
     UBS_REQUIRE(ld_pg >= 3 * H && ld_pg % 4 == 0 && (!a.d.tarmac() || (ld_pv >= a.d.Vp() && ld_pv % 4 == 0)), "ubs_agent_seq2_fwd: bad leading dimensions");
     UBS_REQUIRE(((uintptr_t)pg % 16) == 0 && ((uintptr_t)pv % 16) == 0, "ubs_agent_seq2_fwd: pv / pg must be 16-byte aligned");
     const int rpt = a.d.rows_per_tile();
+    static const bool use_mma = [] { const char* e = getenv("UBS_SEQ2_MMA"); return !(e && e[0] == '0'); }();
+    if (use_mma && mma::fwd_supported(a.d) && ld_pg % 2 == 0 && ld_pv % 2 == 0) {
+        // tensor-core window kernel (mma.sync 3xTF32); UBS_SEQ2_MMA=0 keeps the FP32 kernel for A/B measurements
+        const size_t sm_mma = (size_t)mma::fwd_layout(a.d).total * sizeof(float);
+        static const cudaError_t rc_attr = cudaFuncSetAttribute(mma::seq2_fwd_mma_kernel,
+                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (rc_attr != cudaSuccess) { ubs::set_error("ubs_agent_seq2_fwd: %s", cudaGetErrorString(rc_attr)); return 1; }
+        mma::seq2_fwd_mma_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), mma::NTM, sm_mma, (cudaStream_t)stream>>>(a);
+        return ubs::check_launch("ubs_agent_seq2_fwd(mma)");
+    }
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

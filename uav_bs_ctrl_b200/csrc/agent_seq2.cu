@@ -397,27 +397,27 @@ __device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint
 __host__ __device__ inline int pad8(int n) { return n + ((8 - n % 32) + 32) % 32; }     // == 8 (mod 32)
 __host__ __device__ inline int pad4(int n) { return n + ((4 - n % 32) + 32) % 32; }     // == 4 (mod 32)
 
-// acc[j] (+)= A[16 x Kd] (shared, row-major, stride lda) . W[Kd x 8] at columns n0[j] (shared, K-major, stride ldw)
-// for NT column tiles of one warp; main / corr keep the hi.hi and the two cross terms apart.
-template <int NT>
-__device__ __forceinline__ void warp_gemm(const float* A, int lda, int Kd, const float* W, int ldw, const int (&n0)[NT],
+// acc[j] (+)= A[16 x KD] . W[KD x 8] at columns n0[j] for NT column tiles of one warp.  A comes PRE-SPLIT (two
+// row-major shared arrays hi / lo, stride LDA: the producer splits each activation once instead of every consumer warp
+// every k-step), W is fp32 K-major (stride LDW) and split on the fly.  main / corr keep the hi.hi and the cross terms
+// apart.  All strides / trip counts are compile-time: every fragment load is [base + immediate].
+template <int NT, int KD, int LDA, int LDW>
+__device__ __forceinline__ void warp_gemm(const float* Ahi, const float* Alo, const float* W, const int (&n0)[NT],
                                           int ntiles, float (&main_)[NT][4], float (&corr)[NT][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-    const float* a0p = A + g * lda + c;
-    const float* a1p = a0p + 8 * lda;
-    for (int k0 = 0; k0 < Kd; k0 += 8) {
-        uint32_t ah[4], al[4];
-        split(a0p[k0], ah[0], al[0]);
-        split(a1p[k0], ah[1], al[1]);
-        split(a0p[k0 + 4], ah[2], al[2]);
-        split(a1p[k0 + 4], ah[3], al[3]);
-        const float* wp = W + (k0 + c) * ldw + g;
+    const uint32_t* ah_p = reinterpret_cast<const uint32_t*>(Ahi) + g * LDA + c;
+    const uint32_t* al_p = reinterpret_cast<const uint32_t*>(Alo) + g * LDA + c;
+    const float* wp = W + c * LDW + g;
+#pragma unroll
+    for (int k0 = 0; k0 < KD; k0 += 8) {
+        const uint32_t ah[4] = {ah_p[k0], ah_p[k0 + 8 * LDA], ah_p[k0 + 4], ah_p[k0 + 8 * LDA + 4]};
+        const uint32_t al[4] = {al_p[k0], al_p[k0 + 8 * LDA], al_p[k0 + 4], al_p[k0 + 8 * LDA + 4]};
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             if (j < ntiles) {
                 uint32_t bh0, bl0, bh1, bl1;
-                split(wp[n0[j]], bh0, bl0);
-                split(wp[n0[j] + 4 * ldw], bh1, bl1);
+                split(wp[k0 * LDW + n0[j]], bh0, bl0);
+                split(wp[(k0 + 4) * LDW + n0[j]], bh1, bl1);
                 mma8(corr[j], al, bh0, bh1);
                 mma8(corr[j], ah, bl0, bl1);
                 mma8(main_[j], ah, bh0, bh1);
@@ -429,30 +429,23 @@ __device__ __forceinline__ void warp_gemm(const float* A, int lda, int Kd, const
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// gates: 1 / (1 + 2^(-x log2 e)) with the hardware exp2 / reciprocal (error ~1e-7, far inside the parity budget);
+// tanh(x) = 2 sigmoid(2x) - 1
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
 
-struct Smem { int wVH, wIC, wHH, bHH, sH, sC, sVSQ, sAl, total; int ldV, ld3, ldh, ldc, ldv; };
-__host__ __device__ inline Smem fwd_layout(const Dims& d) {
-    Smem s{};
-    const int H = d.H, H3 = 3 * H, Vp = d.Vp();
-    s.ldV = pad8(Vp); s.ld3 = pad8(H3); s.ldh = pad4(H); s.ldc = pad4(d.M > 0 ? d.M : 4); s.ldv = pad4(Vp > 0 ? Vp : 4);
-    int o = 0;
-    auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
-    s.wVH = take(d.tarmac() ? H * s.ldV : 0);
-    s.wIC = take(d.tarmac() ? d.M * s.ld3 : 0);
-    s.wHH = take(H * s.ld3);
-    s.bHH = take(H3);
-    s.sH = take(R * s.ldh);
-    s.sC = take(d.tarmac() ? R * s.ldc : 0);
-    s.sVSQ = take(d.tarmac() ? R * s.ldv : 0);
-    s.sAl = take(d.tarmac() ? R * d.U : 0);
-    s.total = o;
-    return s;
-}
-__host__ __device__ inline bool fwd_supported(const Dims& d) {
-    if (!(d.H == 32 || d.H == 64)) return false;
-    if (d.tarmac() && (d.M % 8 || d.M < 8 || d.Vp() % 8 || d.Vp() / 8 > 16)) return false;
-    return (size_t)fwd_layout(d).total * sizeof(float) <= 227 * 1024;
-}
+template <int H, int M, int VP>
+struct Lay {                                      // shared-memory layout (float offsets), all compile-time
+    static constexpr bool TM = M > 0;
+    static constexpr int H3 = 3 * H;
+    static constexpr int ldV = VP + ((8 - VP % 32) + 32) % 32, ld3 = H3 + ((8 - H3 % 32) + 32) % 32;
+    static constexpr int ldh = H + ((4 - H % 32) + 32) % 32, ldc = M + ((4 - M % 32) + 32) % 32;
+    static constexpr int ldv = VP + ((4 - VP % 32) + 32) % 32;
+    static constexpr int wVH = 0, wIC = wVH + (TM ? H * ldV : 0), wHH = wIC + (TM ? M * ld3 : 0), bHH = wHH + H * ld3;
+    static constexpr int sHh = bHH + H3, sHl = sHh + R * ldh, sCh = sHl + R * ldh, sCl = sCh + (TM ? R * ldc : 0);
+    static constexpr int sVSQ = sCl + (TM ? R * ldc : 0), sAl = sVSQ + (TM ? R * ldv : 0), sMk = sAl + (TM ? R * 16 : 0);
+    static constexpr int total = sMk + 2 * R;
+};
 
 __device__ __forceinline__ void copy_padded(float* dst, int ld_dst, const float* __restrict__ src, int rows, int cols) {
     const int c4 = cols >> 2;
@@ -462,19 +455,32 @@ __device__ __forceinline__ void copy_padded(float* dst, int ld_dst, const float*
     }
 }
 
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Step schedule (the dependent chain is  h -> vsq -> attention -> c -> gi -> gates -> h'; gh only needs h):
+//   S1  warps 0 .. Vp/8-1 : one vsq column tile each (pv + h W_vsq_h^T) -> shared memory
+//   S2  comm warps        : attention -> c            ||   gate warps : gh = h W_hh^T + b_hh   (off the critical path)
+//   S3  gate warps        : gi = pg + c W_ih_c^T, GRU gates on the fragments, h' -> shared (pre-split) / global
+//                                                     ||   comm warps : prefetch pv / masks of step t + 1
+// Producer -> consumer hand-offs use bar.arrive / bar.sync pairs (ids 2, 3) so that producers never wait.
+template <int H, int M, int VP>
 __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
     extern __shared__ __align__(16) float sm[];
-    const Dims d = a.d;
-    const int H = d.H, H3 = 3 * H, M = d.M, K = d.K, U = d.U, Vp = d.Vp();
-    const bool tm = d.tarmac();
-    const Smem L = fwd_layout(d);
-    float* wVH = sm + L.wVH; float* wIC = sm + L.wIC; float* wHH = sm + L.wHH; float* bHH = sm + L.bHH;
-    float* sH = sm + L.sH; float* sC = sm + L.sC; float* sVSQ = sm + L.sVSQ; float* sAl = sm + L.sAl;
-    if (tm) { copy_padded(wVH, L.ldV, a.w0, H, Vp); copy_padded(wIC, L.ld3, a.w1, M, H3); }
-    copy_padded(wHH, L.ld3, a.w2, H, H3);
+    using L = Lay<H, M, VP>;
+    constexpr bool tm = L::TM;
+    constexpr int H3 = 3 * H, Vp = VP;
+    const int K = a.d.K, U = a.d.U;
+    float* wVH = sm + L::wVH; float* wIC = sm + L::wIC; float* wHH = sm + L::wHH; float* bHH = sm + L::bHH;
+    float* sHh = sm + L::sHh; float* sHl = sm + L::sHl; float* sCh = sm + L::sCh; float* sCl = sm + L::sCl;
+    float* sVSQ = sm + L::sVSQ; float* sAl = sm + L::sAl;
+    uint32_t* sMk = reinterpret_cast<uint32_t*>(sm + L::sMk);              // [2][R] talk masks, double buffered
+    if (tm) { copy_padded(wVH, L::ldV, a.w0, H, Vp); copy_padded(wIC, L::ld3, a.w1, M, H3); }
+    copy_padded(wHH, L::ld3, a.w2, H, H3);
     for (int i = threadIdx.x; i < H3; i += NTM) bHH[i] = __ldg(a.b_hh + i);
 
-    const int rpt = d.rows_per_tile();
+    const int rpt = a.d.rows_per_tile();
     const int64_t row0 = (int64_t)blockIdx.x * rpt;
     const int n_valid = (int)min((int64_t)rpt, a.N - row0);
     const int64_t n = a.N;
@@ -483,158 +489,183 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const bool gate_warp = warp < NGATE && warp < H / 8;
     const bool comm_warp = warp >= NGATE;
-    const int cw = warp - NGATE, ct = threadIdx.x - NGATE * 32;           // comm warp / thread index
-    const int NCT = (NW - NGATE) * 32;
+    const int ct = threadIdx.x - NGATE * 32;                               // comm thread index
+    constexpr int NCT = (NW - NGATE) * 32;
     const int r0 = g, r1 = g + 8;                                          // fragment rows of this lane
     const bool v0 = r0 < n_valid, v1 = r1 < n_valid;
     const int chb = 8 * warp + 2 * c;                                      // gate warps: first of this lane's 2 channels
+    constexpr int vtiles = tm ? Vp / 8 : 0;
+    static_assert(vtiles <= NW, "one vsq column tile per warp");
+    const bool vsq_warp = warp < vtiles;
 
-    for (int i = threadIdx.x; i < R * L.ldh; i += NTM) {
-        const int r = i / L.ldh, f = i - r * L.ldh;
-        sH[i] = (r < n_valid && f < H) ? __ldg(a.h0 + (row0 + r) * H + f) : 0.f;
+    for (int i = threadIdx.x; i < R * L::ldh; i += NTM) {
+        const int r = i / L::ldh, f = i - r * L::ldh;
+        const float v = (r < n_valid && f < H) ? __ldg(a.h0 + (row0 + r) * H + f) : 0.f;
+        uint32_t hi, lo;
+        split(v, hi, lo);
+        sHh[i] = __uint_as_float(hi); sHl[i] = __uint_as_float(lo);
     }
     float hreg[4] = {0.f, 0.f, 0.f, 0.f};                                  // h[r0][chb], h[r0][chb+1], h[r1][chb], h[r1][chb+1]
     if (gate_warp) {
         if (v0) { hreg[0] = __ldg(a.h0 + (row0 + r0) * H + chb); hreg[1] = __ldg(a.h0 + (row0 + r0) * H + chb + 1); }
         if (v1) { hreg[2] = __ldg(a.h0 + (row0 + r1) * H + chb); hreg[3] = __ldg(a.h0 + (row0 + r1) * H + chb + 1); }
     }
-    const int vtiles = tm ? Vp / 8 : 0;
-    const int my_vt = comm_warp ? ((cw < vtiles) + (cw + 8 < vtiles)) : 0;
-    const int vn0[2] = {8 * cw, 8 * (cw + 8)};
-    float pvr[2][4];                                                       // comm warps: pv fragments of the coming step
+    float pvr[1][4] = {{0.f, 0.f, 0.f, 0.f}};                              // vsq warps: pv fragment of the coming step
+    float pgr[3][4];                                                       // gate warps: pg fragments of the coming step
     auto load_pv = [&](int t) {
-        const float* pv = a.pv + (size_t)t * n * a.ld_pv;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            pvr[j][0] = pvr[j][1] = pvr[j][2] = pvr[j][3] = 0.f;
-            if (j < my_vt) {
-                const int col = vn0[j] + 2 * c;
-                if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r0) * a.ld_pv + col)); pvr[j][0] = t2.x; pvr[j][1] = t2.y; }
-                if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r1) * a.ld_pv + col)); pvr[j][2] = t2.x; pvr[j][3] = t2.y; }
-            }
+        if (vsq_warp) {
+            const float* pv = a.pv + (size_t)t * n * a.ld_pv;
+            const int col = 8 * warp + 2 * c;
+            pvr[0][0] = pvr[0][1] = pvr[0][2] = pvr[0][3] = 0.f;
+            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r0) * a.ld_pv + col)); pvr[0][0] = t2.x; pvr[0][1] = t2.y; }
+            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r1) * a.ld_pv + col)); pvr[0][2] = t2.x; pvr[0][3] = t2.y; }
         }
     };
-    if (comm_warp && tm) load_pv(0);
+    auto load_pg = [&](int t) {
+        const float* pg = a.pg + (size_t)t * n * a.ld_pg;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int col = j * H + chb;
+            pgr[j][0] = pgr[j][1] = pgr[j][2] = pgr[j][3] = 0.f;
+            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r0) * a.ld_pg + col)); pgr[j][0] = t2.x; pgr[j][1] = t2.y; }
+            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r1) * a.ld_pg + col)); pgr[j][2] = t2.x; pgr[j][3] = t2.y; }
+        }
+    };
+    auto load_mask = [&](int t) {
+        if (tm && ct >= 0 && ct < R) sMk[(t & 1) * R + ct] = ct < n_valid ? __ldg(a.mask + (size_t)t * n + row0 + ct) : 0u;
+    };
+    if (tm) load_pv(0);
+    if (gate_warp) load_pg(0);
+    load_mask(0);
     __syncthreads();
 
     for (int t = 0; t < a.T; ++t) {
-        const float* pg = a.pg + (size_t)t * n * a.ld_pg;
+        // ---- S1: vsq = pv + h W_vsq_h^T, one column tile per warp
+        if (tm && vsq_warp) {
+            float corr[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+            const int vn0[1] = {8 * warp};
+            warp_gemm<1, H, L::ldh, L::ldV>(sHh, sHl, wVH, vn0, 1, pvr, corr);
+            const int col = vn0[0] + 2 * c;
+            const float2 lo2 = make_float2(pvr[0][0] + corr[0][0], pvr[0][1] + corr[0][1]);
+            const float2 hi2 = make_float2(pvr[0][2] + corr[0][2], pvr[0][3] + corr[0][3]);
+            *reinterpret_cast<float2*>(sVSQ + r0 * L::ldv + col) = lo2;
+            *reinterpret_cast<float2*>(sVSQ + r1 * L::ldv + col) = hi2;
+            if (training) {
+                float* sv = a.sv_vsq + (size_t)t * n * Vp;
+                if (v0) *reinterpret_cast<float2*>(sv + (row0 + r0) * Vp + col) = lo2;
+                if (v1) *reinterpret_cast<float2*>(sv + (row0 + r1) * Vp + col) = hi2;
+            }
+        }
         float gh[3][4], gi[3][4];
-        if (gate_warp) {
-            // ---- gi initialisers (global, needed after phase A: the loads fly during the gh product)
+        if (!comm_warp) {
+            if (tm) bar_arrive(2, NTM);                     // vsq tile handed to the comm warps; go on with gh
+            if (gate_warp) {
+                // ---- S2 (gate warps): gh = h W_hh^T + b_hh
+                float corr[3][4];
+                const int n0[3] = {8 * warp, H + 8 * warp, 2 * H + 8 * warp};
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int col = j * H + chb;
-                gi[j][0] = gi[j][1] = gi[j][2] = gi[j][3] = 0.f;
-                if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r0) * a.ld_pg + col)); gi[j][0] = t2.x; gi[j][1] = t2.y; }
-                if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r1) * a.ld_pg + col)); gi[j][2] = t2.x; gi[j][3] = t2.y; }
-            }
-            // ---- phase A: gh = h W_hh^T + b_hh
-            float corr[3][4];
-            const int n0[3] = {8 * warp, H + 8 * warp, 2 * H + 8 * warp};
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float b0 = bHH[n0[j] + 2 * c], b1 = bHH[n0[j] + 2 * c + 1];
-                gh[j][0] = b0; gh[j][1] = b1; gh[j][2] = b0; gh[j][3] = b1;
-                corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
-            }
-            warp_gemm<3>(sH, L.ldh, H, wHH, L.ld3, n0, 3, gh, corr);
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) gh[j][q] += corr[j][q];
-        } else if (comm_warp && tm) {
-            // ---- phase A': vsq = pv + h W_vsq_h^T  ->  shared memory (+ saved for the backward)
-            float corr[2][4];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
-            warp_gemm<2>(sH, L.ldh, H, wVH, L.ldV, vn0, my_vt, pvr, corr);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j < my_vt) {
-                    const int col = vn0[j] + 2 * c;
-                    const float2 lo2 = make_float2(pvr[j][0] + corr[j][0], pvr[j][1] + corr[j][1]);
-                    const float2 hi2 = make_float2(pvr[j][2] + corr[j][2], pvr[j][3] + corr[j][3]);
-                    *reinterpret_cast<float2*>(sVSQ + r0 * L.ldv + col) = lo2;
-                    *reinterpret_cast<float2*>(sVSQ + r1 * L.ldv + col) = hi2;
-                    if (training) {
-                        float* sv = a.sv_vsq + (size_t)t * n * Vp;
-                        if (v0) *reinterpret_cast<float2*>(sv + (row0 + r0) * Vp + col) = lo2;
-                        if (v1) *reinterpret_cast<float2*>(sv + (row0 + r1) * Vp + col) = hi2;
-                    }
+                for (int j = 0; j < 3; ++j) {
+                    const float b0 = bHH[n0[j] + 2 * c], b1 = bHH[n0[j] + 2 * c + 1];
+                    gh[j][0] = b0; gh[j][1] = b1; gh[j][2] = b0; gh[j][3] = b1;
+                    corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
                 }
+                warp_gemm<3, H, L::ldh, L::ld3>(sHh, sHl, wHH, n0, 3, gh, corr);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { gh[j][q] += corr[j][q]; gi[j][q] = pgr[j][q]; }
             }
-            bar_sync(1, NCT);
-            // ---- block attention (TarMAC.forward: u_dot_v / key_size, edge_softmax, u_mul_e + sum)
-            const uint32_t* mk = a.mask + (size_t)t * n;
-            for (int p = ct; p < R * U; p += NCT) {
-                const int r = p / U, i = p - r * U;
+            if (tm) bar_sync(3, NTM);                       // c is ready
+        } else if (tm) {
+            bar_sync(2, NTM);                               // every vsq tile is in shared memory
+            // ---- S2 (comm warps): block attention (TarMAC.forward: u_dot_v / key_size, edge_softmax, u_mul_e + sum).
+            // 16 lanes per row, lane i < U scores source i; the softmax runs on shuffles inside the 16-lane group.
+            {
+                const int r = ct >> 4, i = ct & 15;
                 float e = -CUDART_INF_F;
-                if (r < n_valid && ((__ldg(mk + row0 + r) >> i) & 1u)) {
-                    const float* sp = sVSQ + ((r / U) * U + i) * L.ldv + M;       // signature of the source
-                    const float* qp = sVSQ + r * L.ldv + M + K;                   // query of the destination
+                if (r < n_valid && i < U && ((sMk[(t & 1) * R + r] >> i) & 1u)) {
+                    const float* sp = sVSQ + ((r / U) * U + i) * L::ldv + M;      // signature of the source
+                    const float* qp = sVSQ + r * L::ldv + M + K;                  // query of the destination
                     float acc = 0.f;
-                    for (int kk = 0; kk < K; ++kk) acc = fmaf(sp[kk], qp[kk], acc);
+                    int kk = 0;
+                    if ((K & 3) == 0) {
+                        for (; kk < K; kk += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(sp + kk);
+                            const float4 q4 = *reinterpret_cast<const float4*>(qp + kk);
+                            acc = fmaf(s4.x, q4.x, acc); acc = fmaf(s4.y, q4.y, acc);
+                            acc = fmaf(s4.z, q4.z, acc); acc = fmaf(s4.w, q4.w, acc);
+                        }
+                    }
+                    for (; kk < K; ++kk) acc = fmaf(sp[kk], qp[kk], acc);
                     e = acc * scale;
                 }
-                sAl[r * U + i] = e;
-            }
-            bar_sync(1, NCT);
-            if (ct < R) {
-                const int r = ct;
-                float mx = -CUDART_INF_F;
-                for (int i = 0; i < U; ++i) mx = fmaxf(mx, sAl[r * U + i]);
-                float den = 0.f;
-                for (int i = 0; i < U; ++i) {
-                    const float e = sAl[r * U + i];
-                    const float pr = e == -CUDART_INF_F ? 0.f : expf(e - mx);
-                    sAl[r * U + i] = pr;
-                    den += pr;
-                }
-                const float inv = den > 0.f ? 1.0f / den : 0.f;
-                for (int i = 0; i < U; ++i) {
-                    const float al = sAl[r * U + i] * inv;
-                    sAl[r * U + i] = al;
+                float mx = e;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, 16));
+                const float pr = e == -CUDART_INF_F ? 0.f : expf(e - mx);
+                float den = pr;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o, 16);
+                const float al = den > 0.f ? pr / den : 0.f;
+                if (i < U) {
+                    sAl[r * 16 + i] = al;
                     if (training && r < n_valid) a.sv_alpha[((size_t)t * n + row0 + r) * U + i] = al;
                 }
             }
             bar_sync(1, NCT);
-            for (int p = ct; p < R * M; p += NCT) {
-                const int r = p / M, m = p - r * M;
+            // c[r][m..m+3] = sum_i alpha[r][i] v[b0 + i][m..m+3]
+            for (int p = ct; p < R * (M / 4); p += NCT) {
+                const int r = p / (M / 4 > 0 ? M / 4 : 1), m = 4 * (p - r * (M / 4));
                 const int b0 = (r / U) * U;
-                float acc = 0.f;
-                if (r < n_valid)
-                    for (int i = 0; i < U; ++i) acc = fmaf(sAl[r * U + i], sVSQ[(b0 + i) * L.ldv + m], acc);
-                sC[r * L.ldc + m] = acc;
-                if (training && r < n_valid) a.sv_c[((size_t)t * n + row0 + r) * M + m] = acc;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < n_valid) {
+#pragma unroll 4
+                    for (int i = 0; i < U; ++i) {
+                        const float al = sAl[r * 16 + i];
+                        const float4 v4 = *reinterpret_cast<const float4*>(sVSQ + (b0 + i) * L::ldv + m);
+                        acc.x = fmaf(al, v4.x, acc.x); acc.y = fmaf(al, v4.y, acc.y);
+                        acc.z = fmaf(al, v4.z, acc.z); acc.w = fmaf(al, v4.w, acc.w);
+                    }
+                }
+                uint32_t hi[4], lo[4];
+                split(acc.x, hi[0], lo[0]); split(acc.y, hi[1], lo[1]); split(acc.z, hi[2], lo[2]); split(acc.w, hi[3], lo[3]);
+                *reinterpret_cast<uint4*>(sCh + r * L::ldc + m) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(sCl + r * L::ldc + m) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if (training && r < n_valid) *reinterpret_cast<float4*>(a.sv_c + ((size_t)t * n + row0 + r) * M + m) = acc;
             }
-            if (t + 1 < a.T) load_pv(t + 1);
+            bar_arrive(3, NTM);                             // c handed to the gate warps
+            load_mask(t + 1 < a.T ? t + 1 : t);             // S3 shadow: next step's masks
         }
-        __syncthreads();                                    // c is ready; everybody has finished reading h
+        if (tm && t + 1 < a.T) load_pv(t + 1);              // in flight during S3 (vsq warps)
         if (gate_warp) {
-            // ---- phase B: gi = pg + c W_ih_c^T, then the GRU gates on the accumulator fragments
+            // ---- S3: gi = pg + c W_ih_c^T, then the GRU gates on the accumulator fragments
             if (tm) {
                 float corr[3][4];
                 const int n0[3] = {8 * warp, H + 8 * warp, 2 * H + 8 * warp};
 #pragma unroll
                 for (int j = 0; j < 3; ++j) corr[j][0] = corr[j][1] = corr[j][2] = corr[j][3] = 0.f;
-                warp_gemm<3>(sC, L.ldc, M, wIC, L.ld3, n0, 3, gi, corr);
+                warp_gemm<3, (M > 0 ? M : 8), L::ldc, L::ld3>(sCh, sCl, wIC, n0, 3, gi, corr);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) gi[j][q] += corr[j][q];
             }
+            if (t + 1 < a.T) load_pg(t + 1);                // next step's initialisers fly during the gates + barrier + S1/S2
             float hn[4], rr[4], zz[4], nn[4];
+            uint32_t hh[4], hl[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                rr[q] = sigmoidf_(gi[0][q] + gh[0][q]);
-                zz[q] = sigmoidf_(gi[1][q] + gh[1][q]);
-                nn[q] = tanhf(fmaf(rr[q], gh[2][q], gi[2][q]));
+                rr[q] = fast_sigmoid(gi[0][q] + gh[0][q]);
+                zz[q] = fast_sigmoid(gi[1][q] + gh[1][q]);
+                nn[q] = fast_tanh(fmaf(rr[q], gh[2][q], gi[2][q]));
                 hn[q] = fmaf(zz[q], hreg[q] - nn[q], nn[q]);
                 hreg[q] = hn[q];
+                split(hn[q], hh[q], hl[q]);
             }
-            *reinterpret_cast<float2*>(sH + r0 * L.ldh + chb) = make_float2(hn[0], hn[1]);
-            *reinterpret_cast<float2*>(sH + r1 * L.ldh + chb) = make_float2(hn[2], hn[3]);
+            *reinterpret_cast<uint2*>(sHh + r0 * L::ldh + chb) = make_uint2(hh[0], hh[1]);
+            *reinterpret_cast<uint2*>(sHh + r1 * L::ldh + chb) = make_uint2(hh[2], hh[3]);
+            *reinterpret_cast<uint2*>(sHl + r0 * L::ldh + chb) = make_uint2(hl[0], hl[1]);
+            *reinterpret_cast<uint2*>(sHl + r1 * L::ldh + chb) = make_uint2(hl[2], hl[3]);
             float* hout = a.h_out + (size_t)t * n * H;
             if (v0) *reinterpret_cast<float2*>(hout + (row0 + r0) * H + chb) = make_float2(hn[0], hn[1]);
             if (v1) *reinterpret_cast<float2*>(hout + (row0 + r1) * H + chb) = make_float2(hn[2], hn[3]);
@@ -653,8 +684,28 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
                 }
             }
         }
-        __syncthreads();                                    // h' is in shared memory for the next step
+        __syncthreads();                                    // h' (and the next masks) are in shared memory
     }
+}
+
+// configurations with a compiled instance: (H, M, Vp)
+template <int H, int M, int VP>
+static int launch_fwd_mma(const Args& a, cudaStream_t st) {
+    static const cudaError_t rc_attr = cudaFuncSetAttribute(seq2_fwd_mma_kernel<H, M, VP>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc_attr != cudaSuccess) { set_error("ubs_agent_seq2_fwd: %s", cudaGetErrorString(rc_attr)); return 1; }
+    const int rpt = a.d.rows_per_tile();
+    const size_t smem = (size_t)Lay<H, M, VP>::total * sizeof(float);
+    seq2_fwd_mma_kernel<H, M, VP><<<(unsigned)((a.N + rpt - 1) / rpt), NTM, smem, st>>>(a);
+    return check_launch("ubs_agent_seq2_fwd(mma)");
+}
+static bool fwd_supported(const Dims& d) {
+    if (d.tarmac()) return (d.H == 64 || d.H == 32) && d.M == 64 && d.Vp() == 96 && d.U <= 16 && d.K <= 32;
+    return d.H == 64 || d.H == 32;
+}
+static int launch_fwd(const Args& a, cudaStream_t st) {
+    if (a.d.tarmac()) return a.d.H == 64 ? launch_fwd_mma<64, 64, 96>(a, st) : launch_fwd_mma<32, 64, 96>(a, st);
+    return a.d.H == 64 ? launch_fwd_mma<64, 0, 0>(a, st) : launch_fwd_mma<32, 0, 0>(a, st);
 }
 
 }  // namespace mma
@@ -709,15 +760,9 @@ extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags,
     UBS_REQUIRE(((uintptr_t)pg % 16) == 0 && ((uintptr_t)pv % 16) == 0, "ubs_agent_seq2_fwd: pv / pg must be 16-byte aligned");
     const int rpt = a.d.rows_per_tile();
     static const bool use_mma = [] { const char* e = getenv("UBS_SEQ2_MMA"); return !(e && e[0] == '0'); }();
-    if (use_mma && mma::fwd_supported(a.d) && ld_pg % 2 == 0 && ld_pv % 2 == 0) {
-        // tensor-core window kernel (mma.sync 3xTF32); UBS_SEQ2_MMA=0 keeps the FP32 kernel for A/B measurements
-        const size_t sm_mma = (size_t)mma::fwd_layout(a.d).total * sizeof(float);
-        static const cudaError_t rc_attr = cudaFuncSetAttribute(mma::seq2_fwd_mma_kernel,
-                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (rc_attr != cudaSuccess) { ubs::set_error("ubs_agent_seq2_fwd: %s", cudaGetErrorString(rc_attr)); return 1; }
-        mma::seq2_fwd_mma_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), mma::NTM, sm_mma, (cudaStream_t)stream>>>(a);
-        return ubs::check_launch("ubs_agent_seq2_fwd(mma)");
-    }
+    // tensor-core window kernel (mma.sync 3xTF32) for the compiled (H, M, K) instances; UBS_SEQ2_MMA=0 keeps the FP32
+    // kernel for A/B measurements
+    if (use_mma && mma::fwd_supported(a.d) && ld_pg % 2 == 0 && ld_pv % 2 == 0) return mma::launch_fwd(a, (cudaStream_t)stream);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(NT) seq2_bwd_kernel(const Args a) {
 // pre-split in shared memory, and every dependent layer would pay a TMEM -> register -> shared-memory round trip; the
 // chain of three dependent 16-row products per timestep is latency-, not throughput-bound.
 namespace mma {
+#ifdef UBS_SEQ2_TRACE
+__device__ long long ubs_trace[8 * 16 * 8];
+#endif
 
 constexpr int NW = 16, NTM = NW * 32, NGATE = 8;
 
@@ -408,22 +411,49 @@ __device__ __forceinline__ void warp_gemm(const float* Ahi, const float* Alo, co
     const uint32_t* ah_p = reinterpret_cast<const uint32_t*>(Ahi) + g * LDA + c;
     const uint32_t* al_p = reinterpret_cast<const uint32_t*>(Alo) + g * LDA + c;
     const float* wp = W + c * LDW + g;
+    // HMMA latency is several issue slots: no two MMAs of a k-step may depend on each other.  The second cross term has
+    // its own accumulator, and a warp with a single tile alternates accumulator sets between even and odd k-steps.
+    constexpr int SETS = NT == 1 ? 2 : 1;
+    float c2[SETS][NT][4], m2[NT][4], c1b[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            m2[j][q] = 0.f; c1b[j][q] = 0.f;
+#pragma unroll
+            for (int s_ = 0; s_ < SETS; ++s_) c2[s_][j][q] = 0.f;
+        }
 #pragma unroll
     for (int k0 = 0; k0 < KD; k0 += 8) {
         const uint32_t ah[4] = {ah_p[k0], ah_p[k0 + 8 * LDA], ah_p[k0 + 4], ah_p[k0 + 8 * LDA + 4]};
         const uint32_t al[4] = {al_p[k0], al_p[k0 + 8 * LDA], al_p[k0 + 4], al_p[k0 + 8 * LDA + 4]};
+        const bool odd = SETS == 2 && ((k0 >> 3) & 1);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             if (j < ntiles) {
                 uint32_t bh0, bl0, bh1, bl1;
                 split(wp[k0 * LDW + n0[j]], bh0, bl0);
                 split(wp[(k0 + 4) * LDW + n0[j]], bh1, bl1);
-                mma8(corr[j], al, bh0, bh1);
-                mma8(corr[j], ah, bl0, bl1);
-                mma8(main_[j], ah, bh0, bh1);
+                if (odd) {
+                    mma8(c1b[j], al, bh0, bh1);
+                    mma8(c2[SETS - 1][j], ah, bl0, bl1);
+                    mma8(m2[j], ah, bh0, bh1);
+                } else {
+                    mma8(corr[j], al, bh0, bh1);
+                    mma8(c2[0][j], ah, bl0, bl1);
+                    mma8(main_[j], ah, bh0, bh1);
+                }
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float cc = corr[j][q] + c2[0][j][q];
+            if (SETS == 2) { cc += c1b[j][q] + c2[SETS - 1][j][q]; main_[j][q] += m2[j][q]; }
+            corr[j][q] = cc;
+        }
 }
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -431,7 +461,10 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 }
 // gates: 1 / (1 + 2^(-x log2 e)) with the hardware exp2 / reciprocal (error ~1e-7, far inside the parity budget);
 // tanh(x) = 2 sigmoid(2x) - 1
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// branch-free (MUFU.EX2 + MUFU.RCP, no slow paths: twelve of them interleave freely); saturates correctly for |x| large
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
 
 template <int H, int M, int VP>
@@ -512,23 +545,26 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
     }
     float pvr[1][4] = {{0.f, 0.f, 0.f, 0.f}};                              // vsq warps: pv fragment of the coming step
     float pgr[3][4];                                                       // gate warps: pg fragments of the coming step
+    // per-thread global addresses of the fragments this lane reads / writes every step (advanced by a stride per step)
+    const size_t o0 = (size_t)(row0 + r0), o1 = (size_t)(row0 + r1);
+    const float* pv0 = tm ? a.pv + o0 * a.ld_pv + 8 * warp + 2 * c : nullptr;
+    const float* pv1 = tm ? a.pv + o1 * a.ld_pv + 8 * warp + 2 * c : nullptr;
+    const size_t st_pv = (size_t)n * a.ld_pv, st_pg = (size_t)n * a.ld_pg;
+    const float* pg0 = a.pg + o0 * a.ld_pg + chb;
+    const float* pg1 = a.pg + o1 * a.ld_pg + chb;
     auto load_pv = [&](int t) {
         if (vsq_warp) {
-            const float* pv = a.pv + (size_t)t * n * a.ld_pv;
-            const int col = 8 * warp + 2 * c;
             pvr[0][0] = pvr[0][1] = pvr[0][2] = pvr[0][3] = 0.f;
-            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r0) * a.ld_pv + col)); pvr[0][0] = t2.x; pvr[0][1] = t2.y; }
-            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv + (row0 + r1) * a.ld_pv + col)); pvr[0][2] = t2.x; pvr[0][3] = t2.y; }
+            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv0 + t * st_pv)); pvr[0][0] = t2.x; pvr[0][1] = t2.y; }
+            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pv1 + t * st_pv)); pvr[0][2] = t2.x; pvr[0][3] = t2.y; }
         }
     };
     auto load_pg = [&](int t) {
-        const float* pg = a.pg + (size_t)t * n * a.ld_pg;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const int col = j * H + chb;
             pgr[j][0] = pgr[j][1] = pgr[j][2] = pgr[j][3] = 0.f;
-            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r0) * a.ld_pg + col)); pgr[j][0] = t2.x; pgr[j][1] = t2.y; }
-            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg + (row0 + r1) * a.ld_pg + col)); pgr[j][2] = t2.x; pgr[j][3] = t2.y; }
+            if (v0) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg0 + t * st_pg + j * H)); pgr[j][0] = t2.x; pgr[j][1] = t2.y; }
+            if (v1) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(pg1 + t * st_pg + j * H)); pgr[j][2] = t2.x; pgr[j][3] = t2.y; }
         }
     };
     auto load_mask = [&](int t) {
@@ -539,7 +575,13 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
     load_mask(0);
     __syncthreads();
 
+#ifdef UBS_SEQ2_TRACE
+#define TR(slot) do { if (blockIdx.x == 0 && lane == 0 && t < 8) ubs_trace[(t * 16 + warp) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
     for (int t = 0; t < a.T; ++t) {
+        TR(0);
         // ---- S1: vsq = pv + h W_vsq_h^T, one column tile per warp
         if (tm && vsq_warp) {
             float corr[1][4] = {{0.f, 0.f, 0.f, 0.f}};
@@ -551,12 +593,13 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
             *reinterpret_cast<float2*>(sVSQ + r0 * L::ldv + col) = lo2;
             *reinterpret_cast<float2*>(sVSQ + r1 * L::ldv + col) = hi2;
             if (training) {
-                float* sv = a.sv_vsq + (size_t)t * n * Vp;
-                if (v0) *reinterpret_cast<float2*>(sv + (row0 + r0) * Vp + col) = lo2;
-                if (v1) *reinterpret_cast<float2*>(sv + (row0 + r1) * Vp + col) = hi2;
+                float* sv = a.sv_vsq + (size_t)t * n * Vp + col;
+                if (v0) *reinterpret_cast<float2*>(sv + o0 * Vp) = lo2;
+                if (v1) *reinterpret_cast<float2*>(sv + o1 * Vp) = hi2;
             }
         }
         float gh[3][4], gi[3][4];
+        TR(1);
         if (!comm_warp) {
             if (tm) bar_arrive(2, NTM);                     // vsq tile handed to the comm warps; go on with gh
             if (gate_warp) {
@@ -575,9 +618,12 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { gh[j][q] += corr[j][q]; gi[j][q] = pgr[j][q]; }
             }
+            TR(2);
             if (tm) bar_sync(3, NTM);                       // c is ready
+            TR(3);
         } else if (tm) {
             bar_sync(2, NTM);                               // every vsq tile is in shared memory
+            TR(2);
             // ---- S2 (comm warps): block attention (TarMAC.forward: u_dot_v / key_size, edge_softmax, u_mul_e + sum).
             // 16 lanes per row, lane i < U scores source i; the softmax runs on shuffles inside the 16-lane group.
             {
@@ -602,17 +648,19 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
                 float mx = e;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, 16));
-                const float pr = e == -CUDART_INF_F ? 0.f : expf(e - mx);
+                const float pr = e == -CUDART_INF_F ? 0.f : __expf(e - mx);
                 float den = pr;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o, 16);
-                const float al = den > 0.f ? pr / den : 0.f;
+                const float al = den > 0.f ? __fdividef(pr, den) : 0.f;
                 if (i < U) {
                     sAl[r * 16 + i] = al;
                     if (training && r < n_valid) a.sv_alpha[((size_t)t * n + row0 + r) * U + i] = al;
                 }
             }
+            TR(3);
             bar_sync(1, NCT);
+            TR(4);
             // c[r][m..m+3] = sum_i alpha[r][i] v[b0 + i][m..m+3]
             for (int p = ct; p < R * (M / 4); p += NCT) {
                 const int r = p / (M / 4 > 0 ? M / 4 : 1), m = 4 * (p - r * (M / 4));
@@ -633,6 +681,7 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
                 *reinterpret_cast<uint4*>(sCl + r * L::ldc + m) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 if (training && r < n_valid) *reinterpret_cast<float4*>(a.sv_c + ((size_t)t * n + row0 + r) * M + m) = acc;
             }
+            TR(5);
             bar_arrive(3, NTM);                             // c handed to the gate warps
             load_mask(t + 1 < a.T ? t + 1 : t);             // S3 shadow: next step's masks
         }
@@ -650,31 +699,34 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) gi[j][q] += corr[j][q];
             }
+            TR(4);
             if (t + 1 < a.T) load_pg(t + 1);                // next step's initialisers fly during the gates + barrier + S1/S2
             float hn[4], rr[4], zz[4], nn[4];
             uint32_t hh[4], hl[4];
 #pragma unroll
+            for (int q = 0; q < 4; ++q) { rr[q] = fast_sigmoid(gi[0][q] + gh[0][q]); zz[q] = fast_sigmoid(gi[1][q] + gh[1][q]); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nn[q] = fast_tanh(fmaf(rr[q], gh[2][q], gi[2][q]));
+#pragma unroll
             for (int q = 0; q < 4; ++q) {
-                rr[q] = fast_sigmoid(gi[0][q] + gh[0][q]);
-                zz[q] = fast_sigmoid(gi[1][q] + gh[1][q]);
-                nn[q] = fast_tanh(fmaf(rr[q], gh[2][q], gi[2][q]));
                 hn[q] = fmaf(zz[q], hreg[q] - nn[q], nn[q]);
                 hreg[q] = hn[q];
                 split(hn[q], hh[q], hl[q]);
             }
+            TR(5);
             *reinterpret_cast<uint2*>(sHh + r0 * L::ldh + chb) = make_uint2(hh[0], hh[1]);
             *reinterpret_cast<uint2*>(sHh + r1 * L::ldh + chb) = make_uint2(hh[2], hh[3]);
             *reinterpret_cast<uint2*>(sHl + r0 * L::ldh + chb) = make_uint2(hl[0], hl[1]);
             *reinterpret_cast<uint2*>(sHl + r1 * L::ldh + chb) = make_uint2(hl[2], hl[3]);
-            float* hout = a.h_out + (size_t)t * n * H;
-            if (v0) *reinterpret_cast<float2*>(hout + (row0 + r0) * H + chb) = make_float2(hn[0], hn[1]);
-            if (v1) *reinterpret_cast<float2*>(hout + (row0 + r1) * H + chb) = make_float2(hn[2], hn[3]);
+            float* hout = a.h_out + (size_t)t * n * H + chb;
+            if (v0) *reinterpret_cast<float2*>(hout + o0 * H) = make_float2(hn[0], hn[1]);
+            if (v1) *reinterpret_cast<float2*>(hout + o1 * H) = make_float2(hn[2], hn[3]);
             if (training) {
-                float* gt = a.sv_gate + (size_t)t * n * 4 * H;
+                float* gt = a.sv_gate + (size_t)t * n * 4 * H + chb;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     if (half == 0 ? v0 : v1) {
-                        float* gp = gt + (row0 + (half == 0 ? r0 : r1)) * 4 * H + chb;
+                        float* gp = gt + (half == 0 ? o0 : o1) * 4 * H;
                         const int q = 2 * half;
                         *reinterpret_cast<float2*>(gp) = make_float2(rr[q], rr[q + 1]);
                         *reinterpret_cast<float2*>(gp + H) = make_float2(zz[q], zz[q + 1]);
@@ -684,7 +736,9 @@ __global__ void __launch_bounds__(NTM, 1) seq2_fwd_mma_kernel(const Args a) {
                 }
             }
         }
+        TR(6);
         __syncthreads();                                    // h' (and the next masks) are in shared memory
+        TR(7);
     }
 }
 
@@ -699,6 +753,17 @@ static int launch_fwd_mma(const Args& a, cudaStream_t st) {
     seq2_fwd_mma_kernel<H, M, VP><<<(unsigned)((a.N + rpt - 1) / rpt), NTM, smem, st>>>(a);
     return check_launch("ubs_agent_seq2_fwd(mma)");
 }
+#ifdef UBS_SEQ2_TRACE
+}  // namespace mma
+}  // namespace seq2
+}  // namespace ubs
+extern "C" UBS_API int ubs_seq2_trace_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, ubs::seq2::mma::ubs_trace, sizeof(long long) * 8 * 16 * 8);
+}
+namespace ubs {
+namespace seq2 {
+namespace mma {
+#endif
 static bool fwd_supported(const Dims& d) {
     if (d.tarmac()) return (d.H == 64 || d.H == 32) && d.M == 64 && d.Vp() == 96 && d.U <= 16 && d.K <= 32;
     return d.H == 64 || d.H == 32;

@@ -753,6 +753,240 @@ static int launch_fwd_mma(const Args& a, cudaStream_t st) {
     seq2_fwd_mma_kernel<H, M, VP><<<(unsigned)((a.N + rpt - 1) / rpt), NTM, smem, st>>>(a);
     return check_launch("ubs_agent_seq2_fwd(mma)");
 }
+// ------------------------------------------------------------------------------------------------ backward (mma)
+// Reverse-time walk with both products of a step on the tensor cores:
+//     carry' = dh z + dgh W_hh      (16 x 3H x H)        warps 0 .. H/8-1, one 8-column tile each, 3H/8 k-steps
+//     dc     = dgi W_ih[:, H:]      (16 x 3H x M)        warps 8 .. 8+M/8-1
+// The warps of the first product own dh: the carry accumulators are the fragments the gate derivatives are computed
+// on, so dh never leaves registers.  dgi / dgh go to shared memory once (fp32, row-major) where they are the A operand
+// of both products AND the staging area from which all threads write the stash rows to global memory with coalesced
+// 16-byte stores.  Weights are kept in FRAGMENT ORDER ([k-step][tile][lane][2]): one conflict-free LDS.64 per MMA
+// B operand.  The attention backward runs one warp per destination row (lanes = source x quarter of the message).
+template <int H, int M, int VP>
+struct LayB {
+    static constexpr bool TM = M > 0;
+    static constexpr int H3 = 3 * H, KS = H3 / 8;                     // k-steps of both products
+    static constexpr int ldg = H3 + ((4 - H3 % 32) + 32) % 32;        // dgi / dgh rows: == 4 (mod 32)
+    static constexpr int ldc = M + 4, ldv = VP + 4;
+    static constexpr int wHH = 0, wIC = wHH + KS * (H / 8) * 64, sDGI = wIC + (TM ? KS * (M / 8) * 64 : 0);
+    static constexpr int sDGH = sDGI + R * ldg, sDC = sDGH + R * ldg, sVSQ = sDC + (TM ? R * ldc : 0);
+    static constexpr int sAl = sVSQ + (TM ? R * ldv : 0), sDS = sAl + (TM ? R * 16 : 0), total = sDS + (TM ? R * 16 : 0);
+};
+
+// W (K x N, K-major, global) -> fragment order in shared memory: dst[((ks * NT + j) * 32 + lane) * 2 + {0,1}] =
+// W[8 ks + c (+4)][8 j + g]  with g = lane / 4, c = lane % 4.
+__device__ __forceinline__ void load_frag_order(float* dst, const float* __restrict__ W, int Kd, int N) {
+    const int NT = N / 8, total = (Kd / 8) * NT * 64;
+    for (int i = threadIdx.x; i < total; i += NTM) {
+        const int e = i & 1, lane = (i >> 1) & 31, j = (i >> 6) % NT, ks = (i >> 6) / NT;
+        dst[i] = __ldg(W + (size_t)(8 * ks + (lane & 3) + 4 * e) * N + 8 * j + (lane >> 2));
+    }
+}
+
+// one 8-column tile: acc (+)= A[16 x 8 KS] (shared fp32 row-major, split on the fly) . Wf (fragment order, tile j of NT)
+template <int KS, int LDA, int NT>
+__device__ __forceinline__ void tile_gemm_f(const float* A, const float* Wf, int j, float (&acc)[4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const float* a0p = A + g * LDA + c;
+    const float2* wp = reinterpret_cast<const float2*>(Wf) + j * 32 + lane;
+    float m[2][4], c1[2][4], c2[2][4];
+#pragma unroll
+    for (int s_ = 0; s_ < 2; ++s_)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { m[s_][q] = 0.f; c1[s_][q] = 0.f; c2[s_][q] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+        split(a0p[8 * ks], ah[0], al[0]);
+        split(a0p[8 * ks + 8 * LDA], ah[1], al[1]);
+        split(a0p[8 * ks + 4], ah[2], al[2]);
+        split(a0p[8 * ks + 8 * LDA + 4], ah[3], al[3]);
+        const float2 w = wp[ks * NT * 32];
+        split(w.x, bh0, bl0);
+        split(w.y, bh1, bl1);
+        mma8(c1[ks & 1], al, bh0, bh1);
+        mma8(c2[ks & 1], ah, bl0, bl1);
+        mma8(m[ks & 1], ah, bh0, bh1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += (m[0][q] + m[1][q]) + ((c1[0][q] + c1[1][q]) + (c2[0][q] + c2[1][q]));
+}
+
+template <int H, int M, int VP>
+__global__ void __launch_bounds__(NTM, 1) seq2_bwd_mma_kernel(const Args a) {
+    extern __shared__ __align__(16) float sm[];
+    using L = LayB<H, M, VP>;
+    constexpr bool tm = L::TM;
+    constexpr int H3 = 3 * H, Vp = VP, Md = M > 0 ? M : 8, Vq = VP > 0 ? VP / 4 : 1;
+    const int K = a.d.K, U = a.d.U;
+    float* wHH = sm + L::wHH; float* wIC = sm + L::wIC; float* sDGI = sm + L::sDGI; float* sDGH = sm + L::sDGH;
+    float* sDC = sm + L::sDC; float* sVSQ = sm + L::sVSQ; float* sAl = sm + L::sAl; float* sDS = sm + L::sDS;
+    load_frag_order(wHH, a.w0, H3, H);
+    if (tm) load_frag_order(wIC, a.w1, H3, M);
+
+    const int rpt = a.d.rows_per_tile();
+    const int64_t row0 = (int64_t)blockIdx.x * rpt;
+    const int n_valid = (int)min((int64_t)rpt, a.N - row0);
+    const int64_t n = a.N;
+    const float scale = tm ? 1.0f / (float)K : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const bool own = warp < H / 8;                                   // carry tile + dh owner
+    const bool dcw = tm && warp >= 8 && warp - 8 < Md / 8;           // dc tile
+    const int r0 = g, r1 = g + 8;
+    const bool v0 = r0 < n_valid, v1 = r1 < n_valid;
+    const int chb = 8 * warp + 2 * c;
+    const size_t o0 = (size_t)(row0 + r0), o1 = (size_t)(row0 + r1);
+
+    float carry[4] = {0.f, 0.f, 0.f, 0.f};                          // dh flowing into step t: (r0,chb) (r0,chb+1) (r1,chb) (r1,chb+1)
+    // prefetched per-step inputs of the owners: gates r z n ghn, previous hidden state, dhq
+    float2 pr_[2][4], ph[2], pq[2];
+    auto prefetch = [&](int t) {
+        const float* gt = a.sv_gate + (size_t)t * n * 4 * H + chb;
+        const float* hp = (t > 0 ? a.h_out + (size_t)(t - 1) * n * H : a.h0) + chb;
+        const float* dq = a.dhq + (size_t)t * n * H + chb;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const bool v = hf == 0 ? v0 : v1;
+            const size_t o = hf == 0 ? o0 : o1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pr_[hf][q] = v ? __ldg(reinterpret_cast<const float2*>(gt + o * 4 * H + q * H)) : make_float2(0.f, 0.f);
+            ph[hf] = v ? __ldg(reinterpret_cast<const float2*>(hp + o * H)) : make_float2(0.f, 0.f);
+            pq[hf] = v ? __ldg(reinterpret_cast<const float2*>(dq + o * H)) : make_float2(0.f, 0.f);
+        }
+    };
+    if (own) prefetch(a.T - 1);
+    __syncthreads();
+
+    for (int t = a.T - 1; t >= 0; --t) {
+        // ---- E1: gate derivatives on the carry fragments -> dgi / dgh (shared, fp32) ; carry <- dh z
+        if (own) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int r = hf == 0 ? r0 : r1;
+                float dgi_[3][2], dnr[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float rr = e ? pr_[hf][0].y : pr_[hf][0].x, zz = e ? pr_[hf][1].y : pr_[hf][1].x;
+                    const float nn = e ? pr_[hf][2].y : pr_[hf][2].x, ghn = e ? pr_[hf][3].y : pr_[hf][3].x;
+                    const float hp = e ? ph[hf].y : ph[hf].x, dq = e ? pq[hf].y : pq[hf].x;
+                    const float gv = carry[2 * hf + e] + dq;
+                    const float dn = gv * (1.0f - zz) * (1.0f - nn * nn);
+                    const float dz = gv * (hp - nn) * zz * (1.0f - zz);
+                    const float dr = dn * ghn * rr * (1.0f - rr);
+                    dgi_[0][e] = dr; dgi_[1][e] = dz; dgi_[2][e] = dn; dnr[e] = dn * rr;
+                    carry[2 * hf + e] = gv * zz;
+                }
+                float* gi_ = sDGI + r * L::ldg + chb;
+                float* gh_ = sDGH + r * L::ldg + chb;
+                *reinterpret_cast<float2*>(gi_) = make_float2(dgi_[0][0], dgi_[0][1]);
+                *reinterpret_cast<float2*>(gi_ + H) = make_float2(dgi_[1][0], dgi_[1][1]);
+                *reinterpret_cast<float2*>(gi_ + 2 * H) = make_float2(dgi_[2][0], dgi_[2][1]);
+                *reinterpret_cast<float2*>(gh_) = make_float2(dgi_[0][0], dgi_[0][1]);
+                *reinterpret_cast<float2*>(gh_ + H) = make_float2(dgi_[1][0], dgi_[1][1]);
+                *reinterpret_cast<float2*>(gh_ + 2 * H) = make_float2(dnr[0], dnr[1]);
+            }
+            if (t > 0) prefetch(t - 1);                  // in flight during the products and the attention backward
+        }
+        if (tm) {                                        // vsq / alpha of this step -> shared memory (used after the products)
+            const float* gv_ = a.sv_vsq + (size_t)t * n * Vp;
+            for (int i = threadIdx.x; i < R * Vq; i += NTM) {
+                const int r = i / Vq, q = i - r * Vq;
+                const float4 v = r < n_valid ? __ldg(reinterpret_cast<const float4*>(gv_ + (row0 + r) * Vp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(sVSQ + r * L::ldv + 4 * q) = v;
+            }
+            const float* ga = a.sv_alpha + (size_t)t * n * U;
+            for (int i = threadIdx.x; i < R * 16; i += NTM) {
+                const int r = i >> 4, j = i & 15;
+                sAl[i] = (r < n_valid && j < U) ? __ldg(ga + (row0 + r) * U + j) : 0.f;
+            }
+        }
+        __syncthreads();                                 // dgi / dgh (and vsq / alpha) are in shared memory
+        {   // stash rows -> global, coalesced (every thread: 16-byte pieces of the 16 x 3H tiles)
+            float* gdgi = a.st_dgi + (size_t)t * n * a.ld_st;
+            float* gdgh = a.st_dgh + (size_t)t * n * a.ld_st;
+            constexpr int Q = H3 / 4;
+            for (int i = threadIdx.x; i < 2 * R * Q; i += NTM) {
+                const int arr = i / (R * Q), rem = i - arr * (R * Q), r = rem / Q, q = rem - r * Q;
+                if (r < n_valid) {
+                    const float4 v = *reinterpret_cast<const float4*>((arr ? sDGH : sDGI) + r * L::ldg + 4 * q);
+                    *reinterpret_cast<float4*>((arr ? gdgh : gdgi) + (row0 + r) * a.ld_st + 4 * q) = v;
+                }
+            }
+        }
+        if (own) {
+            tile_gemm_f<L::KS, L::ldg, H / 8>(sDGH, wHH, warp, carry);                       // carry' = dh z + dgh W_hh
+        } else if (dcw) {
+            float dc[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_gemm_f<L::KS, L::ldg, Md / 8>(sDGI, wIC, warp - 8, dc);                      // dc = dgi W_ih[:, H:]
+            const int col = 8 * (warp - 8) + 2 * c;
+            *reinterpret_cast<float2*>(sDC + r0 * L::ldc + col) = make_float2(dc[0], dc[1]);
+            *reinterpret_cast<float2*>(sDC + r1 * L::ldc + col) = make_float2(dc[2], dc[3]);
+        }
+        if (tm) {
+            __syncthreads();                             // dc is in shared memory
+            // ---- attention backward, one warp per destination row: lanes = (source i, quarter of the message)
+            {
+                const int r = warp, b0 = (r / U) * U;
+                const int Up = U <= 8 ? 8 : 16, parts = 32 / Up;       // lanes per source
+                const int i = lane / parts, part = lane - i * parts;
+                float acc = 0.f;
+                if (r < n_valid && i < U) {
+                    const float* dcp = sDC + r * L::ldc;
+                    const float* vp = sVSQ + (b0 + i) * L::ldv;
+                    for (int m = 4 * part; m < M; m += 4 * parts) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(dcp + m);
+                        const float4 v4 = *reinterpret_cast<const float4*>(vp + m);
+                        acc = fmaf(d4.x, v4.x, acc); acc = fmaf(d4.y, v4.y, acc);
+                        acc = fmaf(d4.z, v4.z, acc); acc = fmaf(d4.w, v4.w, acc);
+                    }
+                }
+                for (int o = parts >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                const float al = (r < n_valid && i < U) ? sAl[r * 16 + i] : 0.f;
+                float tot = part == 0 ? al * acc : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (part == 0 && i < 16) sDS[r * 16 + i] = al * (acc - tot);
+            }
+            __syncthreads();
+            float* gdv = a.st_dvsq + (size_t)t * n * a.ld_st;
+            for (int p = threadIdx.x; p < R * Vp; p += NTM) {
+                const int r = p / (Vp > 0 ? Vp : 1), f = p - r * Vp;
+                const int b0 = (r / U) * U, li = r - b0;
+                float acc = 0.f;
+                if (r < n_valid) {
+                    if (f < M) {
+                        for (int j = 0; j < U; ++j) acc = fmaf(sAl[(b0 + j) * 16 + li], sDC[(b0 + j) * L::ldc + f], acc);
+                    } else if (f < M + K) {
+                        for (int j = 0; j < U; ++j) acc = fmaf(sDS[(b0 + j) * 16 + li], sVSQ[(b0 + j) * L::ldv + f + K], acc);
+                        acc *= scale;
+                    } else if (f < M + 2 * K) {
+                        for (int i = 0; i < U; ++i) acc = fmaf(sDS[r * 16 + i], sVSQ[(b0 + i) * L::ldv + f - K], acc);
+                        acc *= scale;
+                    }
+                    gdv[(row0 + r) * a.ld_st + f] = acc;
+                }
+            }
+        }
+        __syncthreads();                                 // shared tiles are free for the next step
+    }
+    if (a.d_h0 != nullptr && own) {
+        if (v0) *reinterpret_cast<float2*>(a.d_h0 + o0 * H + chb) = make_float2(carry[0], carry[1]);
+        if (v1) *reinterpret_cast<float2*>(a.d_h0 + o1 * H + chb) = make_float2(carry[2], carry[3]);
+    }
+}
+
+template <int H, int M, int VP>
+static int launch_bwd_mma(const Args& a, cudaStream_t st) {
+    static const cudaError_t rc_attr = cudaFuncSetAttribute(seq2_bwd_mma_kernel<H, M, VP>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc_attr != cudaSuccess) { set_error("ubs_agent_seq2_bwd: %s", cudaGetErrorString(rc_attr)); return 1; }
+    const int rpt = a.d.rows_per_tile();
+    const size_t smem = (size_t)LayB<H, M, VP>::total * sizeof(float);
+    seq2_bwd_mma_kernel<H, M, VP><<<(unsigned)((a.N + rpt - 1) / rpt), NTM, smem, st>>>(a);
+    return check_launch("ubs_agent_seq2_bwd(mma)");
+}
+static int launch_bwd(const Args& a, cudaStream_t st);
+
 #ifdef UBS_SEQ2_TRACE
 }  // namespace mma
 }  // namespace seq2
@@ -771,6 +1005,10 @@ static bool fwd_supported(const Dims& d) {
 static int launch_fwd(const Args& a, cudaStream_t st) {
     if (a.d.tarmac()) return a.d.H == 64 ? launch_fwd_mma<64, 64, 96>(a, st) : launch_fwd_mma<32, 64, 96>(a, st);
     return a.d.H == 64 ? launch_fwd_mma<64, 0, 0>(a, st) : launch_fwd_mma<32, 0, 0>(a, st);
+}
+static int launch_bwd(const Args& a, cudaStream_t st) {
+    if (a.d.tarmac()) return a.d.H == 64 ? launch_bwd_mma<64, 64, 96>(a, st) : launch_bwd_mma<32, 64, 96>(a, st);
+    return a.d.H == 64 ? launch_bwd_mma<64, 0, 0>(a, st) : launch_bwd_mma<32, 0, 0>(a, st);
 }
 
 }  // namespace mma
@@ -857,6 +1095,10 @@ extern "C" UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags,
     a.ld_st = ld_stash;
     UBS_REQUIRE(ld_stash >= 3 * H, "ubs_agent_seq2_bwd: bad stash leading dimension");
     const int rpt = a.d.rows_per_tile();
+    static const bool use_mma = [] { const char* e = getenv("UBS_SEQ2_MMA"); return !(e && e[0] == '0'); }();
+    if (use_mma && mma::fwd_supported(a.d) && ld_stash % 4 == 0 && ((uintptr_t)st_dgi % 16) == 0 && ((uintptr_t)st_dgh % 16) == 0 &&
+        ((uintptr_t)sv_vsq % 16) == 0)
+        return mma::launch_bwd(a, (cudaStream_t)stream);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(seq2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -98,6 +98,27 @@ UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst, const int3
                       int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout,
                       int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
 
+/* Training pair with SAVED ATTENTION SCORES: the forward additionally writes the raw score of every (edge slot, head) —
+ * scores[(s * st_scores + e) * heads + k] for CSR slot e of segment s (16 bytes per edge at 4 heads) — and the backward
+ * reads them instead of recomputing the H-channel score of every edge (its pass over the edges then only forms
+ * exp(score - max) / sum and the softmax gradient).  scores == NULL: same as ubs_gatv2_seg_fwd / _bwd.  16-byte aligned. */
+UBS_API int ubs_gatv2_seg_fwd_scores(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                      const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                      const float* attn, const float* W_res, const float* b_res,
+                      float* out, float* smax, float* ssum, float* scores, int64_t st_scores,
+                      int64_t n_seg, int64_t n_dst_seg, int64_t n_edges,
+                      int64_t st_xsrc, int64_t st_xdst, int64_t st_ip, int64_t st_sidx, int64_t ld_out,
+                      int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
+UBS_API int ubs_gatv2_seg_bwd_scores(const float* x_src, const float* x_dst, const int32_t* indptr, const int32_t* src_idx,
+                      const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
+                      const float* attn, const float* W_res, const float* b_res,
+                      const float* out, const float* grad_out, const float* smax, const float* ssum,
+                      const float* scores, int64_t st_scores,
+                      float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                      int64_t n_seg, int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst,
+                      int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout,
+                      int F_s, int F_d, int heads, int D, float negative_slope, int flags, void* stream);
+
 /* ---- GATv2 attention + aggregation on pre-projected features, general CSR (wide inputs / synthetic sweep) ---------
  * After the library GEMMs el = fc_src(h_src) (n_src,H), er = fc_dst(h_dst) (n_dst,H), res = res_fc(h_dst) (nullable):
  *   out[v] = act( sum_e softmax_e( <attn_k, leaky_relu(el[u_e] + er[v])_k> ) * el[u_e] + res[v] ),  H = heads*D in

@@ -38,6 +38,8 @@ _PROTOS = {
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),
     "ubs_gatv2_seg_bwd": (C.c_int, [_F] * 19 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
+    "ubs_gatv2_seg_fwd_scores": (C.c_int, [_F] * 15 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
+    "ubs_gatv2_seg_bwd_scores": (C.c_int, [_F] * 16 + [_i64] + [_F] * 4 + [_i64] * 9 + [_int] * 4 + [_flt, _int, _ptr]),
     "ubs_gat_aggr_fwd": (C.c_int, [_F] * 9 + [_i64, _i64, _int, _int, _flt, _int, _ptr]),
     "ubs_gat_aggr_bwd_workspace": (_i64, [_i64, _int, _int]),
     "ubs_gat_aggr_bwd": (C.c_int, [_F] * 15 + [_i64, _i64, _int, _int, _flt, _int, _ptr]),

@@ -512,6 +512,10 @@ class GnnAgent(nn.Module):
         for c in convs:
             params += [c.fc_src.weight, c.fc_src.bias, c.fc_dst.weight, c.fc_dst.bias, c.attn, c.res_fc.weight,
                        c.res_fc.bias]
+        if not th.is_grad_enabled():
+            # inside Function.forward the grad mode is always off, so the op decides from requires_grad what to save for
+            # a backward: under no_grad (act step, target network) hand it detached parameters — no stats, no scores
+            params = [p.detach() for p in params]
         c0 = convs[0]
         out = ops.SegmentEncode.apply(arena.buf, specs, arena.ptr("x_agent", t0), W, L.F_ag, T, L.N, c0._num_heads,
                                       c0._out_feats, c0._negative_slope, ops.GAT_RESIDUAL | ops.GAT_RELU, *params)

@@ -35,6 +35,9 @@ struct GatArgs {
     // x_src / x_dst / indptr / src_idx start seg * st_* elements after the base pointers (indptr is segment-local).
     // Outputs are indexed by the global destination id with row strides ld_out / ld_gout.
     int n_dst_seg; long long st_xsrc, st_xdst, st_ip, st_sidx; int ld_out, ld_gout;
+    // optional per-(edge slot, head) raw attention scores: written by a training forward, read by the backward instead of
+    // recomputing them (16 B per edge at 4 heads instead of ~5 H FMAs); slot e of segment s lives at (s * st_score + e) * heads
+    float* score; const float* score_in; long long st_score;
 };
 
 template <int FS>
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
         }
         for (int e = beg + li; e < end; e += GS * EPL) {
             float x[EPL][FS];
+            float sk[EPL][HPW];
             bool ok[EPL];
 #pragma unroll
             for (int j = 0; j < EPL; ++j) {
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
                 }
 #pragma unroll
                 for (int j = 0; j < EPL; ++j) {
+                    sk[j][k] = s[j];
                     if (ok[j]) {
                         const float mn = fmaxf(m[k], s[j]);
                         const float sc = __expf(m[k] - mn);
@@ -208,6 +213,20 @@ __global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatArgs a) {
 #pragma unroll
                         for (int f = 0; f < FS; ++f) acc[k][f] = fmaf(acc[k][f], sc, p * x[j][f]);
                         m[k] = mn;
+                    }
+                }
+            }
+            if (a.score != nullptr) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    if (ok[j]) {
+                        float* sp = a.score + ((size_t)seg * a.st_score + (e + j * GS)) * HEADS + k0;
+                        if constexpr (HPW == 4) *reinterpret_cast<float4*>(sp) = make_float4(sk[j][0], sk[j][1], sk[j][2], sk[j][3]);
+                        else if constexpr (HPW == 2) *reinterpret_cast<float2*>(sp) = make_float2(sk[j][0], sk[j][1]);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < HPW; ++k) sp[k] = sk[j][k];
+                        }
                     }
                 }
             }
@@ -591,11 +610,26 @@ __global__ void __launch_bounds__(128) gatv2_bwd2_kernel(const GatArgs a) {
                     for (int f = 0; f < FS; ++f) x[f] = xr[f];
                 }
                 xs[warp][lane] = make_float4(x[0], x[1], x[2], x[3]);
+                float sv[HEADS] = {};
+                if (a.score_in != nullptr && lane < cnt) {       // scores saved by the forward: no recomputation
+                    const float* sp = a.score_in + ((size_t)seg * a.st_score + (e0 + lane)) * HEADS;
+                    if constexpr (HEADS == 4) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(sp));
+                        sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < HEADS; ++k) sv[k] = __ldg(sp + k);
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < HEADS; ++k) {
                     const float4 h0 = hc[warp][k][0], h1 = hc[warp][k][1];
+                    float s;
+                    if (a.score_in != nullptr) {
+                        s = sv[k];
+                    } else {
                     const float4 pl = *reinterpret_cast<const float4*>(hP + k * 8);
-                    float s = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
+                    s = fmaf(hP[k * 8 + 5], xv1, fmaf(hP[k * 8 + 4], xv0, hP[k * 8 + 6]));
                     s = fmaf(pl.x, x[0], s);
                     if constexpr (FS > 1) s = fmaf(pl.y, x[1], s);
                     if constexpr (FS > 2) s = fmaf(pl.z, x[2], s);
@@ -612,6 +646,7 @@ __global__ void __launch_bounds__(128) gatv2_bwd2_kernel(const GatArgs a) {
                         if constexpr (FS > 2) z = fmaf(w.z, x[2], z);
                         if constexpr (FS > 3) z = fmaf(w.w, x[3], z);
                         s = fmaf(cc.y, fabsf(z), s);
+                    }
                     }
                     const float alpha = lane < cnt ? __expf(s - h1.z) * h1.w : 0.f;
                     float da = h0.y;
@@ -846,8 +881,21 @@ extern "C" UBS_API int ubs_gatv2_seg_fwd(const float* x_src, const float* x_dst,
                                  int64_t n_edges, int64_t st_xsrc, int64_t st_xdst, int64_t st_ip, int64_t st_sidx,
                                  int64_t ld_out, int F_s, int F_d, int heads, int D, float negative_slope, int flags,
                                  void* stream) {
+    return ubs_gatv2_seg_fwd_scores(x_src, x_dst, indptr, src_idx, W_src, b_src, W_dst, b_dst, attn, W_res, b_res, out, smax,
+                                    ssum, nullptr, 0, n_seg, n_dst_seg, n_edges, st_xsrc, st_xdst, st_ip, st_sidx, ld_out, F_s,
+                                    F_d, heads, D, negative_slope, flags, stream);
+}
+
+extern "C" UBS_API int ubs_gatv2_seg_fwd_scores(const float* x_src, const float* x_dst, const int32_t* indptr,
+                                 const int32_t* src_idx, const float* W_src, const float* b_src, const float* W_dst,
+                                 const float* b_dst, const float* attn, const float* W_res, const float* b_res,
+                                 float* out, float* smax, float* ssum, float* scores, int64_t st_scores, int64_t n_seg,
+                                 int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst, int64_t st_ip,
+                                 int64_t st_sidx, int64_t ld_out, int F_s, int F_d, int heads, int D, float negative_slope,
+                                 int flags, void* stream) {
     const int64_t n_dst = n_seg * n_dst_seg;
     if (int rc = ubs::check_shape("ubs_gatv2_fwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(scores == nullptr || (((uintptr_t)scores % 16) == 0 && st_scores >= 0), "ubs_gatv2_fwd: scores must be 16-byte aligned");
     UBS_REQUIRE(n_seg >= 1 && n_dst_seg >= 0 && ld_out >= heads * D, "ubs_gatv2_fwd: bad segment description");
     UBS_REQUIRE(F_s != 4 || st_xsrc % 4 == 0, "ubs_gatv2_fwd: segment stride breaks 16-byte row alignment");
     UBS_REQUIRE(F_s != 2 || st_xsrc % 2 == 0, "ubs_gatv2_fwd: segment stride breaks 8-byte row alignment");
@@ -863,6 +911,7 @@ extern "C" UBS_API int ubs_gatv2_seg_fwd(const float* x_src, const float* x_dst,
     a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
     a.n_dst_seg = (int)(n_dst_seg > 0 ? n_dst_seg : 1); a.st_xsrc = st_xsrc; a.st_xdst = st_xdst; a.st_ip = st_ip;
     a.st_sidx = st_sidx; a.ld_out = (int)ld_out; a.ld_gout = (int)ld_out;
+    a.score = scores; a.st_score = st_scores;
     int rc = 0;
     UBS_DISPATCH_FS_HEADS(ubs::launch_fwd, a, n_edges, (cudaStream_t)stream)
     return rc;
@@ -893,8 +942,24 @@ extern "C" UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst,
                                  int64_t n_seg, int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst,
                                  int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout, int F_s, int F_d,
                                  int heads, int D, float negative_slope, int flags, void* stream) {
+    return ubs_gatv2_seg_bwd_scores(x_src, x_dst, indptr, src_idx, W_src, b_src, W_dst, b_dst, attn, W_res, b_res, out, grad_out,
+                                    smax, ssum, nullptr, 0, grad_params, grad_x_src, grad_x_dst, workspace, n_seg, n_dst_seg,
+                                    n_edges, st_xsrc, st_xdst, st_ip, st_sidx, ld_out, ld_gout, F_s, F_d, heads, D,
+                                    negative_slope, flags, stream);
+}
+
+extern "C" UBS_API int ubs_gatv2_seg_bwd_scores(const float* x_src, const float* x_dst, const int32_t* indptr,
+                                 const int32_t* src_idx, const float* W_src, const float* b_src, const float* W_dst,
+                                 const float* b_dst, const float* attn, const float* W_res, const float* b_res,
+                                 const float* out, const float* grad_out, const float* smax, const float* ssum,
+                                 const float* scores, int64_t st_scores,
+                                 float* grad_params, float* grad_x_src, float* grad_x_dst, float* workspace,
+                                 int64_t n_seg, int64_t n_dst_seg, int64_t n_edges, int64_t st_xsrc, int64_t st_xdst,
+                                 int64_t st_ip, int64_t st_sidx, int64_t ld_out, int64_t ld_gout, int F_s, int F_d,
+                                 int heads, int D, float negative_slope, int flags, void* stream) {
     const int64_t n_dst = n_seg * n_dst_seg;
     if (int rc = ubs::check_shape("ubs_gatv2_bwd", F_s, F_d, heads, D, negative_slope)) return rc;
+    UBS_REQUIRE(scores == nullptr || ((uintptr_t)scores % 16) == 0, "ubs_gatv2_bwd: scores must be 16-byte aligned");
     UBS_REQUIRE(n_seg >= 1 && n_dst_seg >= 0 && ld_out >= heads * D && ld_gout >= heads * D, "ubs_gatv2_bwd: bad segment description");
     UBS_REQUIRE(F_s != 4 || st_xsrc % 4 == 0, "ubs_gatv2_bwd: segment stride breaks 16-byte row alignment");
     UBS_REQUIRE(F_s != 2 || st_xsrc % 2 == 0, "ubs_gatv2_bwd: segment stride breaks 8-byte row alignment");
@@ -917,6 +982,7 @@ extern "C" UBS_API int ubs_gatv2_seg_bwd(const float* x_src, const float* x_dst,
     a.n_dst = (int)n_dst; a.F_d = F_d; a.D = D; a.slope = negative_slope; a.flags = flags;
     a.n_dst_seg = (int)(n_dst_seg > 0 ? n_dst_seg : 1); a.st_xsrc = st_xsrc; a.st_xdst = st_xdst; a.st_ip = st_ip;
     a.st_sidx = st_sidx; a.ld_out = (int)ld_out; a.ld_gout = (int)ld_gout;
+    a.score_in = grad_x_src == nullptr ? scores : nullptr; a.st_score = st_scores;
     int rc = 0;
     UBS_DISPATCH_FS_HEADS(ubs::launch_bwd, a, H, st)
     if (rc) return rc;

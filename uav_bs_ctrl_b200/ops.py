@@ -493,6 +493,7 @@ class AgentSequence(th.autograd.Function):
 # Strided-segment relation encoder (ubs_gatv2_seg_fwd / ubs_gatv2_seg_bwd): all timesteps of an arena in one launch per
 # relation, every relation writing its own column block of ONE (rows, R*H) output buffer.
 _SIDE_STREAMS = {}
+SAVE_SCORES = True      # training forward keeps the per-(edge, head) attention scores for the backward (False: recompute)
 
 
 def _side_stream(dev, i):
@@ -531,9 +532,14 @@ class SegmentEncode(th.autograd.Function):
         dev = keepalive.device
         H, R = heads * D, len(specs)
         rows = n_seg * n_dst_seg
-        need_grad = any(p is not None and p.requires_grad for p in params)
+        need_grad = any(p is not None and p.requires_grad for p in params)      # callers detach under no_grad
         out = th.empty(rows, R * H, dtype=th.float32, device=dev)
         stats = th.empty(R, 2, rows, heads, dtype=th.float32, device=dev) if need_grad else None
+        # training: the raw attention score of every (edge slot, head) is kept for the backward (16 B per edge at 4
+        # heads — as much as the source row itself) instead of being recomputed from the H-channel projection
+        caps = [max(int(sp.n_edges_hint) // max(int(n_seg), 1), 1) for sp in specs]
+        scores = [th.empty(n_seg * cap * heads, dtype=th.float32, device=dev) if (need_grad and SAVE_SCORES) else None
+                  for cap in caps]
         ps = [_f32c(p.detach()) if p is not None else None for p in params]
         # small launches (the act step) cannot fill the chip: relations run side by side on a forked stream
         fork = R > 1 and rows <= 8192 and TIMER is None
@@ -550,18 +556,19 @@ class SegmentEncode(th.autograd.Function):
                 side.wait_stream(cur)
             with _timed("gatv2_fwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, need_grad)), \
                     (th.cuda.stream(side) if side is not None else _nullctx()):
-                _lib.check(lib.ubs_gatv2_seg_fwd(
+                _lib.check(lib.ubs_gatv2_seg_fwd_scores(
                     sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
                     out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]) if need_grad else None,
-                    _lib.ptr(stats[r, 1]) if need_grad else None, n_seg, n_dst_seg, sp.n_edges_hint, sp.st_xsrc, st_xdst,
-                    sp.st_ip, sp.st_sidx, R * H, sp.F_s, F_d, heads, D, float(slope), int(flags), _lib.stream()),
-                    "ubs_gatv2_seg_fwd")
+                    _lib.ptr(stats[r, 1]) if need_grad else None, _lib.ptr(scores[r]), caps[r], n_seg, n_dst_seg,
+                    sp.n_edges_hint, sp.st_xsrc, st_xdst, sp.st_ip, sp.st_sidx, R * H, sp.F_s, F_d, heads, D, float(slope),
+                    int(flags), _lib.stream()), "ubs_gatv2_seg_fwd")
             if side is not None:
                 sides.append(side)
         for side in sides:
             cur.wait_stream(side)
         if need_grad:
             ctx.save_for_backward(keepalive, out, stats, *[p for p in ps if p is not None])
+            ctx.scores, ctx.caps = scores, caps                 # plain buffers (not autograd inputs / outputs)
             ctx.cfg = (specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, float(slope), int(flags),
                        [p is not None for p in params], [None if p is None else tuple(p.shape) for p in params])
         return out
@@ -584,10 +591,11 @@ class SegmentEncode(th.autograd.Function):
             gparams = th.empty(Pn, dtype=th.float32, device=dev)
             ws = th.empty(int(lib.ubs_gatv2_bwd_workspace(rows, sp.F_s, F_d, heads, D)), dtype=th.float32, device=dev)
             with _timed("gatv2_bwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, True)):
-                _lib.check(lib.ubs_gatv2_seg_bwd(
+                _lib.check(lib.ubs_gatv2_seg_bwd_scores(
                     sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
                     out.data_ptr() + 4 * r * H, grad_out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]),
-                    _lib.ptr(stats[r, 1]), _lib.ptr(gparams), None, None, _lib.ptr(ws), n_seg, n_dst_seg,
+                    _lib.ptr(stats[r, 1]), _lib.ptr(ctx.scores[r]), ctx.caps[r], _lib.ptr(gparams), None, None, _lib.ptr(ws),
+                    n_seg, n_dst_seg,
                     sp.n_edges_hint, sp.st_xsrc, st_xdst, sp.st_ip, sp.st_sidx, R * H, R * H, sp.F_s, F_d, heads, D,
                     slope, flags, _lib.stream()), "ubs_gatv2_seg_bwd")
             o = 0

@@ -303,31 +303,35 @@ def run_ours(a):
         from uav_bs_ctrl_b200 import envs as E
         m = E.DenseHotSpot(n_ubs=U, n_grps=G // 5, gts_per_grp=5, episode_limit=T)
         env = E.MultiUbsCoverageVecEnv(n_envs=B, device=dev, map=m)
-        pool = env.make_layout_pool(4, seed0=10_000 * (rank + 1))
-        cyc = [0]
+        env.seed = 10_000 * (rank + 1)
 
         def full_step():
             learner.begin_sequence(arena)
-            env.reset(arena, 0, layouts=pool[cyc[0] % len(pool)])
-            cyc[0] += 1
+            env.reset(arena, 0)                       # fresh layouts every episode: sampled on the device (Philox)
             learner.rollout_arena(env, arena, eps)
             return learner.update_arena(arena, sync=False)
 
         ms_f, launches_f, _ = timed(full_step, a.steps, a.warmup)
         deg = float(arena.sec("ip_seen")[:, -1].float().mean()) / (B * U)
         ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        env.reset(arena, 0, layouts=pool[0])
+        er0, er1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        er0.record()
+        for _ in range(10):
+            env.reset(arena, 0)
+        er1.record()
         ev0.record()
         for t in range(T):                                # env alone: 2 kernels per step (step + pack), eager launches
             env.step(arena, t)
         ev1.record()
         th.cuda.synchronize()
         env_us = 1e3 * ev0.elapsed_time(ev1) / T
+        reset_us = 1e3 * er0.elapsed_time(er1) / 10
         full = {"value": world * B * T * a.steps / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / a.steps,
                 "gpu_launches": int(launches_f), "mean_seen_degree": deg, "env_step_us": env_us,
-                "env_steps_per_sec_env_alone": B / (env_us * 1e-6),
+                "env_steps_per_sec_env_alone": B / (env_us * 1e-6), "reset_us": reset_us,
                 "env": f"device-resident MultiUbsCoverageEnv, DenseHotSpot {U} UBS x {G} GT (maps.py:83-113), "
-                       f"episode_limit {T}, eps-greedy {eps}; resets from a pool of {len(pool)} x {B} RNG-matched layouts; "
+                       f"episode_limit {T}, eps-greedy {eps}; every episode starts from fresh layouts sampled on the device "
+                       f"(ubs_env_sample_layouts, Philox); "
                        "one CUDA graph per rollout" + ("" if learner.args.cuda_graphs else " (graphs off)")}
         if rank == 0 and world == 1 and not a.no_cpu:
             full["cpu_env_port"] = cpu_env_port(m, B)

@@ -12,7 +12,8 @@
  * Arithmetic follows the reference statement by statement, including which intermediates numpy keeps in float32 and
  * which in float64 (NEP 50 promotion, numpy >= 2; see tests/golden/make_env_golden.py) and numpy's pairwise
  * summation order; argsort ties are broken by index (a valid np.argsort; numpy's own tie order is unspecified).
- * Initial layouts (maps.py set_positions: host RNG) are sampled by the caller and passed to ubs_env_reset.
+ * Initial layouts (maps.py set_positions) come either from the caller (RNG-matched host sampler) or from
+ * ubs_env_sample_layouts (device, Philox).
  *
  * Conventions: as ubs_gnn.h — device pointers owned by the caller, asynchronous launches on `stream`, 0 = success,
  * message through ubs_last_error().  The config struct is passed by host pointer and copied into the launch.
@@ -73,6 +74,24 @@ typedef struct {
                           -1: not stored */
     int64_t ld_flat;   /* row pitch in floats, >= 2 + G (2 + 3 + fair_service) ... see envs.flat_obs_dim(); the pad is zero */
 } ubs_env_packet;
+
+/* Parameters of the map's reset distribution (maps.py set_positions) for the on-device layout sampler. */
+typedef struct {
+    int32_t kind;        /* 0: Map (uniform grid points), 1: HotSpot (maps.py:64-77), 2: DenseHotSpot (maps.py:97-113) */
+    int32_t n_ubs, n_gts, n_grps, gts_per_grp; /* n_grps / gts_per_grp: DenseHotSpot only */
+    int32_t ubs_cells;   /* UBS grid points per axis: range_pos (kind 0) or range_pos // min_dist */
+    int32_t range_spot;  /* hotspot side in cells: smallest s with s*s >= n_gts (HotSpot) / n_grps (DenseHotSpot) */
+    int32_t spot_cells;  /* hotspot origins per axis: range_pos // min_dist // range_spot */
+    double min_dist, range_pos, r_cov;
+} ubs_env_layout_cfg;
+
+/* reset(), first half, on the device: samples pos_ubs / pos_gts / prior of all B instances from the map's reset
+ * distribution (Map / HotSpot / DenseHotSpot.set_positions + np.random.permutation(n_gts), mubs_cov.py:96-98) with a
+ * counter-based Philox stream addressed by (seed, instance, episode): same distribution as the reference's host RNG,
+ * not the same draws (the RNG-matched host sampler stays available through the caller: envs.sample_layouts).
+ * Follow with ubs_env_reset.                                                                                        */
+UBS_ENV_API int ubs_env_sample_layouts(const ubs_env_layout_cfg* layout, const ubs_env_state* st, uint64_t seed,
+                                       uint32_t episode, int64_t B, void* stream);
 
 /* Words of device scratch ubs_env_step / ubs_env_reset need for B envs (staging of the per-env compacted rows). */
 UBS_ENV_API int64_t ubs_env_scratch_words(const ubs_env_cfg* cfg, int64_t B);

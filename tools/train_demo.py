@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """End-to-end training on the device: MADRQN (graph observation encoder + TarMAC) on B parallel instances of the
 device-resident MultiUbsCoverageEnv, reference loop cadence (algos/madrqn/run.py:81-99: act / env.step every step, one
-BPTT update per episode window), epsilon annealed 1 -> 0.05, fresh RNG-matched layouts every episode from a
-pre-sampled pool.  Prints one JSON object with the mean episode return (info['EpRet'], mubs_cov.py:113-119) per block
+BPTT update per episode window), epsilon annealed 1 -> 0.05, fresh layouts every episode sampled on the device
+(ubs_env_sample_layouts).  Prints one JSON object with the mean episode return (info['EpRet'], mubs_cov.py:113-119) per block
 of cycles — the check that env + encoder + comm + learner work together, not a benchmark.
 
     python tools/train_demo.py --cycles 1500 > gpurun_out/train_demo.json
@@ -27,7 +27,6 @@ def main():
     ap.add_argument("--cycles", type=int, default=1500)
     ap.add_argument("--envs", type=int, default=256)
     ap.add_argument("--map", default="4ubs")
-    ap.add_argument("--pool", type=int, default=24)
     ap.add_argument("--block", type=int, default=100)
     ap.add_argument("--lr", type=float, default=5e-4)
     a = ap.parse_args()
@@ -42,9 +41,7 @@ def main():
     th.manual_seed(0)
     learner = MultiAgentQLearner(env.get_env_info(), args)
     arena = learner.new_arena(env.cfg.n_gts)
-    t0 = time.perf_counter()
-    pool = env.make_layout_pool(a.pool, seed0=1)
-    t_pool = time.perf_counter() - t0
+    env.seed = 1
     curve, acc = [], []
     decay = int(0.6 * a.cycles)
     th.cuda.synchronize()
@@ -52,7 +49,7 @@ def main():
     for c in range(a.cycles):
         eps = max(0.05, 1.0 - 0.95 * c / max(decay, 1))
         learner.begin_sequence(arena)
-        env.reset(arena, 0, layouts=pool[c % len(pool)])
+        env.reset(arena, 0)                                        # fresh layouts, sampled on the device
         learner.rollout_arena(env, arena, eps)
         acc.append(env.buf.info[:, 0].mean())                      # EpRet of the finished episodes (device scalar)
         out = learner.update_arena(arena, sync=False)
@@ -64,7 +61,7 @@ def main():
     th.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(json.dumps({"map": a.map, "envs": B, "T": T, "cycles": a.cycles, "env_steps": a.cycles * B * T,
-                      "seconds": round(dt, 2), "env_steps_per_sec": a.cycles * B * T / dt, "layout_pool_seconds": round(t_pool, 2),
+                      "seconds": round(dt, 2), "env_steps_per_sec": a.cycles * B * T / dt,
                       "curve": curve}, indent=1))
 
 

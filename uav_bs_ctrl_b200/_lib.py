@@ -63,6 +63,7 @@ _PROTOS = {
     # include/ubs_env.h (config / state / packet structs travel by host pointer)
     "ubs_env_scratch_words": (_i64, [_ptr, _i64]),
     "ubs_env_phase_clocks": (C.c_int, [_ptr]),
+    "ubs_env_sample_layouts": (C.c_int, [_ptr, _ptr, C.c_uint64, C.c_uint32, _i64, _ptr]),
     "ubs_env_reset": (C.c_int, [_ptr, _ptr, _ptr, _I, _i64, _ptr]),
     "ubs_env_step": (C.c_int, [_ptr, _ptr, _I, _ptr, _I, _i64, _ptr]),
 }

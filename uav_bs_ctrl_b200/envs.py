@@ -45,6 +45,12 @@ class UbsEnvPacket(C.Structure):
                                                                    "ld_flat")]
 
 
+class UbsEnvLayoutCfg(C.Structure):
+    """``ubs_env_layout_cfg`` of ``include/ubs_env.h``: the map's reset distribution for the device sampler."""
+    _fields_ = [(n, C.c_int32) for n in ("kind", "n_ubs", "n_gts", "n_grps", "gts_per_grp", "ubs_cells", "range_spot",
+                                         "spot_cells")] + [(n, C.c_double) for n in ("min_dist", "range_pos", "r_cov")]
+
+
 # ------------------------------------------------------------------------------------------------------ maps
 def _select_from_cube(rng: _pyrandom.Random, n_els, min_val, max_val, n_dims=2):
     """``envs/common.py:13-16``: ``random.sample`` over ``product(arange(min, max), ...)``.  ``random.sample`` only looks
@@ -210,6 +216,28 @@ def make_cfg(m: Map, fair_service: bool = True, avoid_collision: bool = True) ->
     return c
 
 
+def make_layout_cfg(m: "Map") -> Optional[UbsEnvLayoutCfg]:
+    """Parameters of ``m.set_positions()`` for ``ubs_env_sample_layouts`` (``maps.py:30-34,64-77,97-113``), or ``None``
+    for maps without a device sampler (``Debug``: fixed positions; ``DenseHotSpotV2``: not in the reference registry)."""
+    c = UbsEnvLayoutCfg()
+    c.n_ubs, c.n_gts, c.range_pos, c.r_cov, c.min_dist = int(m.n_ubs), int(m.n_gts), float(m.range_pos), float(m.r_cov), 200.0
+    if type(m) is Map:
+        c.kind, c.ubs_cells = 0, int(m.range_pos)
+        return c
+    if type(m) in (HotSpot, DenseHotSpot):
+        dense = type(m) is DenseHotSpot
+        n = m.n_grps if dense else m.n_gts
+        range_spot = 1
+        while range_spot * range_spot < n:                   # "ensure sufficient area to hold GTs" (maps.py:69-70,102-103)
+            range_spot += 1
+        c.kind = 2 if dense else 1
+        c.n_grps, c.gts_per_grp = (int(m.n_grps), int(m.gts_per_grp)) if dense else (0, 0)
+        c.ubs_cells = int(m.range_pos // c.min_dist)
+        c.range_spot, c.spot_cells = range_spot, int(m.range_pos // c.min_dist // range_spot)
+        return c
+    return None
+
+
 def flat_obs_dim(cfg: UbsEnvCfg) -> int:
     """2 own features + G rows of (flag, dx, dy, rate[, avg rate]) + (U-1) rows of (flag, dx, dy)  (``mubs_cov.py:247-278``)."""
     return 2 + cfg.n_gts * (5 if cfg.fair_service else 4) + (cfg.n_ubs - 1) * 3
@@ -313,6 +341,8 @@ class MultiUbsCoverageVecEnv:
         self.n_agents, self.n_actions = self.cfg.n_ubs, self.cfg.n_actions
         self.episode_limit = self.cfg.episode_limit
         self._episode = 0
+        self.layout_cfg = make_layout_cfg(self.map)           # None: no device sampler for this map
+        self.seed = 0                                          # key of the device sampler's Philox stream
 
     # reference-shaped metadata (env_wrappers.py:117-120, :62-63)
     def get_env_info(self, o="gnn"):
@@ -354,17 +384,33 @@ class MultiUbsCoverageVecEnv:
         if arena.buf.device != self.device:
             raise RuntimeError("arena and env must live on the same CUDA device")
 
-    def reset(self, arena, slot: int = 0, seeds: Optional[Sequence[int]] = None, layouts=None):
-        """New episode in every instance.  ``seeds[b]`` plays the role of the reference's global seed for instance b
-        (default: a running counter); ``layouts = (pos_ubs, pos_gts, prior)`` overrides the sampling."""
+    def reset(self, arena, slot: int = 0, seeds: Optional[Sequence[int]] = None, layouts=None, device: Optional[bool] = None):
+        """New episode in every instance.  Where the initial layouts come from:
+
+        * default (``device=None`` -> True when the map has a device sampler): ``ubs_env_sample_layouts`` draws them on
+          the GPU from the map's reset distribution (Philox stream keyed by ``self.seed``, the instance and a running
+          episode counter) — nothing touches the host, the call is two kernel launches;
+        * ``seeds=[...]`` (or ``device=False``): the RNG-matched host sampler — ``seeds[b]`` plays the role of the
+          reference's global seed for instance b (``random.seed(s); np.random.seed(s)``), bit-identical layouts to the
+          reference's ``reset()`` but ~0.3 ms of python per instance;
+        * ``layouts=(pos_ubs, pos_gts, prior)``: caller-provided."""
         from . import _lib
         self._check(arena)
-        if layouts is None:
-            if seeds is None:
-                seeds = [self._episode * self.n_envs + b for b in range(self.n_envs)]
-            layouts = sample_layouts(self.map, seeds)
+        if device is None:
+            device = layouts is None and seeds is None and self.layout_cfg is not None
+        if device:
+            if self.layout_cfg is None:
+                raise ValueError(f"map {type(self.map).__name__} has no device sampler: pass seeds= or layouts=")
+            _lib.check(self._lib.ubs_env_sample_layouts(C.byref(self.layout_cfg), C.byref(self._state), int(self.seed),
+                                                        int(self._episode) & 0xFFFFFFFF, self.n_envs, _lib.stream()),
+                       "ubs_env_sample_layouts")
+        else:
+            if layouts is None:
+                if seeds is None:
+                    seeds = [self._episode * self.n_envs + b for b in range(self.n_envs)]
+                layouts = sample_layouts(self.map, seeds)
+            self.buf.set_layout(*layouts)
         self._episode += 1
-        self.buf.set_layout(*layouts)
         pk = packet_struct(arena.layout, arena.buf[slot])
         _lib.check(self._lib.ubs_env_reset(C.byref(self.cfg), C.byref(self._state), C.byref(pk),
                                            self.buf.scratch.data_ptr(), self.n_envs, _lib.stream()), "ubs_env_reset")

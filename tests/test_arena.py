@@ -155,3 +155,31 @@ def test_learner_arena_cycle_matches_graph_object_cycle(use_graphs):
     with th.no_grad():
         q_ref, _ = L2.policy_net(graphs[0], th.zeros(B * U, 64, device="cuda"))
     assert float((ar.acts[0] != q_ref.argmax(1)).float().mean()) < 0.01
+
+
+def test_replay_ring_keeps_the_order_of_the_reference_deque():
+    """``ArenaReplay`` mirrors ``ReplayBuffer`` (reference ``algos/madrqn/buffer.py:7-42``): capacity-bounded, oldest window
+    overwritten first, ``sample`` draws distinct stored windows."""
+    import random
+    from uav_bs_ctrl_b200.arena import ArenaReplay
+    L = PacketLayout(2, 2, 3)
+    made = []
+
+    def make():
+        made.append(SequenceArena(L, 3, 4, "cpu"))
+        return made[-1]
+    rp = ArenaReplay(make, capacity=3)
+    assert len(rp) == 0 and rp.windows() == []
+    for k in range(5):
+        ar = rp.next_arena()
+        ar.acts.fill_(k)                                   # tag the window
+        rp.commit()
+        assert len(rp) == min(k + 1, 3)
+    assert len(made) == 3, "arenas are allocated once and recycled"
+    assert [int(a.acts[0, 0]) for a in rp.windows()] == [2, 3, 4], "oldest first, like deque(maxlen=capacity)"
+    random.seed(0)
+    picked = rp.sample(2)
+    assert len(picked) == 2 and picked[0] is not picked[1] and all(p in rp.windows() for p in picked)
+    with pytest.raises(ValueError):
+        rp.sample(4)
+    assert rp.nbytes() == 3 * (made[0].buf.numel() * 4 + made[0].h.numel() * 4 + made[0].acts.numel() * 8)

@@ -271,3 +271,44 @@ def test_qlearner_matches_reference_drqn():
         assert float(d.abs().max()) <= 2.01 * cfg["lr"]
         if bool(big.any()):
             assert float(d[big].abs().max()) <= 2e-3 * cfg["lr"], f"drqn AdamW step of {k}"
+
+
+@pytest.mark.parametrize("tag", ["exp3", "qmix"])
+def test_replay_ring_update_matches_reference_learner(tag):
+    """Device-resident replay (``ArenaReplay``): the reference loop's sequences are stored as single-env windows of a
+    ring of arenas in the order the reference's ``ReplayBuffer`` received them; ``update_arena`` on the windows at the
+    indices the reference sampled (``random.sample(memory, batch_size)``, ``buffer.py:37-39``) must reproduce the
+    reference ``update()`` — off-policy replay with ``batch_size > 1`` on the fast path."""
+    case = ref_golden()[f"learner/{tag}"]
+    cfg, T = case["config"], case["max_seq_len"]
+    lr = _learner(case, n_envs=1, cuda_graphs=False)
+    p0 = {k: p.detach().clone() for k, p in lr.policy_net.named_parameters()}
+    n_seq = len(case["transitions"]) // T
+    replay = lr.new_replay(case["n_gts"], capacity=n_seq)
+    tr = case["transitions"]
+    for k in range(n_seq):
+        b = ref_learner_batch(case, [k])
+        ar = replay.next_arena()
+        for t in range(T + 1):
+            s = b["steps"][t]
+            rew = done = bad = None
+            if t > 0:
+                rew = tr[k * T + t - 1]["rew"].float().unsqueeze(0)
+                done = th.tensor([float(tr[k * T + t - 1]["done"])])
+                bad = th.tensor([float(tr[k * T + t - 1]["bad"])])
+            pk = ObsPacket(ar.layout).fill_from_dense(s["agent"], s["gt"], s["ubs"], s["adj"], rew=rew, done=done, bad=bad,
+                                                     state=None if b["states"] is None else b["states"][t])
+            ar.load(t, pk)
+        ar.h[0].copy_(b["h0"])
+        ar.h[1].copy_(b["h1"])
+        ar.acts[:T].copy_(b["acts"].squeeze(-1))
+        replay.commit()
+    assert len(replay) == n_seq
+    windows = replay.windows()
+    out = lr.update_arena([windows[i] for i in case["sample_idx"][0]])
+    _check_update(case, lr, out, p0, f"{tag}/replay")
+    # the ring overwrites its oldest window and keeps the order of the reference's deque
+    first = replay.next_arena()
+    assert first is windows[0]
+    replay.commit()
+    assert replay.windows()[-1] is windows[0] and replay.windows()[0] is windows[1]

@@ -533,13 +533,21 @@ class GnnAgent(nn.Module):
         return self.enc.enc(arena.flat_obs(t0, T))
 
     def arena_sequence(self, arena, t0, T, h0):
-        """``forward_sequence`` over arena slots ``t0 .. t0+T-1`` (with autograd when enabled)."""
-        dims = self.arena_dims(arena)
+        """``forward_sequence`` over arena slots ``t0 .. t0+T-1`` (with autograd when enabled).  ``arena`` may be a LIST of
+        arenas (sampled replay windows, ``arena.ArenaReplay``): every window is encoded in place and the recurrent kernels
+        run over the agent rows of all of them (``h0`` = their initial hidden states concatenated in list order)."""
+        arenas = list(arena) if isinstance(arena, (list, tuple)) else [arena]
+        dims = self.arena_dims(arenas[0])
         if dims is None:
             raise NotImplementedError("arena path needs the fused step configuration (and, for the MLP encoder, an arena "
                                       "with flattened observations)")
-        xin = self._arena_xin(arena, t0, T) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t0, T)
-        mask = arena.sec("mask")[t0:t0 + T].contiguous() if dims.tarmac else None
+        graph_enc = isinstance(self.enc, GraphObservationEncoder)
+        xs = [self._arena_xin(a, t0, T) if graph_enc else self._arena_flat_x(a, t0, T) for a in arenas]
+        xin = xs[0] if len(xs) == 1 else th.cat(xs, 1)
+        mask = None
+        if dims.tarmac:
+            ms = [a.sec("mask")[t0:t0 + T] for a in arenas]
+            mask = (ms[0] if len(ms) == 1 else th.cat(ms, 1)).contiguous()
         return self._run_sequence(dims, xin, h0.contiguous(), mask)
 
     @th.no_grad()

@@ -199,3 +199,46 @@ class SequenceArena:
         """``(T, B, 1)``: ``(1 - bad_mask) * done`` (reference ``learner.py:91``)."""
         d, b = self.sec("done")[1:T + 1], self.sec("bad")[1:T + 1]
         return ((1 - b) * d).reshape(T, self.layout.B, 1)
+
+
+class ArenaReplay:
+    """Device-resident sequence replay: a ring of ``capacity`` sequence arenas (reference ``ReplayBuffer``,
+    ``algos/madrqn/buffer.py:7-42``, whose entries are Python lists of host graph objects).
+
+    One arena = one finished window of ``max_seq_len`` transitions of the learner's ``n_envs`` env instances, i.e.
+    ``n_envs`` of the reference's sequences; it never leaves HBM.  ``sample(batch_size)`` draws ``batch_size`` stored
+    windows uniformly without replacement (``random.sample``, ``buffer.py:37-39``) and returns them as a list — pointer
+    selection, no copies; ``learner.update_arena(list)`` encodes every selected window in place with the
+    strided-segment kernels and runs the recurrent window kernels over all their agent rows at once.
+    HBM budget: ``capacity`` x arena bytes (142 MB per exp3 window of 256 envs: ~1 000 windows fit 180 GB)."""
+
+    def __init__(self, make_arena, capacity: int):
+        self._make, self.capacity = make_arena, int(capacity)
+        self._ring, self._filled, self._next = [], 0, 0
+
+    def next_arena(self) -> "SequenceArena":
+        """The arena the next window is collected into (the oldest stored window once the ring is full)."""
+        if len(self._ring) < self.capacity and self._next == len(self._ring):
+            self._ring.append(self._make())
+        return self._ring[self._next]
+
+    def commit(self):
+        """The window in ``next_arena()`` is complete (``buffer.py:30-35``: the sequence is appended to memory)."""
+        self._next = (self._next + 1) % self.capacity
+        self._filled = min(self._filled + 1, self.capacity)
+
+    def __len__(self):
+        return self._filled
+
+    def windows(self):
+        """Stored windows, oldest first (the order of the reference's ``deque``)."""
+        if self._filled < self.capacity:
+            return self._ring[:self._filled]
+        return self._ring[self._next:] + self._ring[:self._next]
+
+    def sample(self, batch_size: int):
+        import random
+        return random.sample(self.windows(), batch_size)
+
+    def nbytes(self) -> int:
+        return sum(a.buf.numel() * 4 + a.h.numel() * 4 + a.acts.numel() * 8 for a in self._ring)

@@ -391,21 +391,31 @@ class MultiAgentQLearner:
         g[0].replay()
         _lib.add_launches(g[1])
 
+    def new_replay(self, n_gts, capacity=None):
+        """Device-resident replay ring of ``capacity`` (default ``args.replay_size``) sequence arenas."""
+        from .arena import ArenaReplay
+        return ArenaReplay(lambda: self.new_arena(n_gts), capacity or self.args.replay_size)
+
     def update_arena(self, arena, sync=True):
-        """One BPTT update on the window held by ``arena`` (same math as ``update``; no graph objects, no re-batching):
-        one strided-segment encoder launch per relation over all T+1 timesteps and one persistent recurrent kernel,
-        for the policy (with grad) and for the target network."""
+        """One BPTT update on the window held by ``arena`` — or on a LIST of windows sampled from an ``ArenaReplay``
+        (``buffer.sample(batch_size)`` + the per-timestep ``cat`` of reference ``learner.py:99-116``, as pointer
+        selection).  Same math as ``update``; no graph objects, no re-batching: one strided-segment encoder launch per
+        relation and window over all T+1 timesteps, and one persistent recurrent kernel over the agent rows of all
+        windows, for the policy (with grad) and for the target network."""
+        arenas = list(arena) if isinstance(arena, (list, tuple)) else [arena]
         T = self.max_seq_len
-        acts = arena.acts[:T].unsqueeze(-1)
-        rews, dones = arena.rewards(T), arena.dones(T)
+        cat = (lambda xs, d: xs[0] if len(xs) == 1 else th.cat(xs, d))
+        acts = cat([a.acts[:T] for a in arenas], 1).unsqueeze(-1)
+        rews, dones = cat([a.rewards(T) for a in arenas], 1), cat([a.dones(T) for a in arenas], 1)
         if self.args.share_reward:
             rews = rews.mean(2, keepdim=True)
-        keep = (1 - arena.sec("done", 1)).repeat_interleave(self.n_agents).unsqueeze(1)     # next_h = (1 - done) * next_h
-        h0, h_targ = arena.h[0], arena.h[1] * keep
-        agent_out, _ = self.policy_net.arena_sequence(arena, 0, T + 1, h0)
+        # next_h = (1 - done) * next_h  (reference cache(), learner.py:90)
+        keep = cat([(1 - a.sec("done", 1)).repeat_interleave(self.n_agents) for a in arenas], 0).unsqueeze(1)
+        h0, h_targ = cat([a.h[0] for a in arenas], 0), cat([a.h[1] for a in arenas], 0) * keep
+        agent_out, _ = self.policy_net.arena_sequence(arenas, 0, T + 1, h0)
         with th.no_grad():
-            target_out, _ = self.target_net.arena_sequence(arena, 1, T, h_targ)
-        states = arena.states(T + 1) if self.mixer is not None else None
+            target_out, _ = self.target_net.arena_sequence(arenas, 1, T, h_targ)
+        states = cat([a.states(T + 1) for a in arenas], 1) if self.mixer is not None else None
         loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones, states)
         return self._optimise(loss, qvals, sync)
 

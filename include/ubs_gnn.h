@@ -179,6 +179,22 @@ UBS_API int ubs_block_mean_fwd(const float* msg, int64_t ld_msg, const uint32_t*
 UBS_API int ubs_block_mean_bwd(const float* grad_out, int64_t ld_go, const uint32_t* mask, float* grad_msg, int64_t ld_gm,
                                int64_t n, int block, int F, void* stream);
 
+/* ---- DiscreteComm message passing over block-diagonal comm graphs (gnn_agents.py:151-193) --------------------------
+ * Per edge u->v and bit k: hard Gumbel-softmax (tau) of the source's encoder logits (n, 2*msg_size: f_enc output per
+ * NODE) plus per-EDGE noise; per destination: element-wise max (OR) over the in-edges, zeros without in-edges.
+ * expo (E, msg_size, 2): Exponential(1) draws in the reference's edge-id order (gumbel = -log expo: what
+ * F.gumbel_softmax consumes); env_edge_offset (n / block) int64: first edge id of every env (exclusive prefix sum of
+ * the envs' edge counts); mask / block as in ubs_block_attn_fwd.  winner (n, 2*msg_size) uint8 (NULL for inference):
+ * local source index of the first maximal mailbox entry per (destination, feature) — torch.max(dim)'s one-winner
+ * gradient — consumed by the backward, which writes grad_logits (n, 2*msg_size), deterministic, no atomics.      */
+UBS_API int ubs_block_bitmax_fwd(const float* logits, int64_t ld_logits, const float* expo, const uint32_t* mask,
+                                 const int64_t* env_edge_offset, float* out, int64_t ld_out, uint8_t* winner,
+                                 int64_t n, int block, int msg_size, float tau, void* stream);
+UBS_API int ubs_block_bitmax_bwd(const float* logits, int64_t ld_logits, const float* expo, const uint32_t* mask,
+                                 const int64_t* env_edge_offset, const uint8_t* winner, const float* grad_out,
+                                 int64_t ld_go, float* grad_logits, int64_t ld_gl, int64_t n, int block, int msg_size,
+                                 float tau, void* stream);
+
 /* ---- GRUCell gate math (nn.GRUCell, gate order r,z,n) given gi = W_ih x + b_ih, gh = W_hh h + b_hh --------- */
 UBS_API int ubs_gru_gates_fwd(const float* gi, const float* gh, const float* h, float* h_out, int64_t n, int H, void* stream);
 /* grad_gi, grad_gh: (n, 3H); grad_h_direct: (n, H) = grad_out * z (the part that does not go through W_hh). */

@@ -219,3 +219,30 @@ def test_block_mean_matches_the_edge_list_path(B, U, F_, p):
     assert float(out[0].abs().max()) == 0.0
     out2 = ops.BlockMean.apply(m_dev, mask.cuda(), U)
     assert th.equal(out, out2)
+
+
+@pytest.mark.parametrize("U,B,M,comm_p", [(8, 6, 64, 0.6), (3, 5, 16, 0.5), (16, 2, 32, 0.8), (8, 4, 64, 0.0), (1, 7, 8, 1.0)])
+def test_block_bitmax_matches_the_edge_list_path(U, B, M, comm_p):
+    """DiscreteComm's fused kernel (per-edge hard Gumbel-softmax + OR over the destination's bit mask, one-winner
+    gradient) against the edge-list formulation with torch ops (mailbox max in edge-id order)."""
+    from uav_bs_ctrl_b200.agents.gnn_agents import _first_max_by_dst
+    a, gt, ubs, adj = synth_dense_obs(B, U, 4, "full", seed=5, comm_p=comm_p)
+    g = build_obs_graph_batch(a, gt, ubs, adj).to(DEV)["talk"]
+    N, E = B * U, g.number_of_edges()
+    gen = th.Generator(device=DEV).manual_seed(3)
+    logits = th.randn(N, 2 * M, device=DEV, generator=gen, requires_grad=True)
+    expo = th.empty(E, M, 2, device=DEV).exponential_(generator=gen)
+    w = th.randn(N, 2 * M, device=DEV, generator=gen)
+    block, mask = g.block_mask()
+    c1 = ops.BlockBitMax.apply(logits, expo, mask, block, 0.5)
+    (c1 * w).sum().backward()
+    g1, logits.grad = logits.grad.clone(), None
+    src, _ = g.edges()
+    lg = logits.index_select(0, src).view(-1, M, 2)
+    y = ((lg - expo.log()) / 0.5).softmax(-1)
+    hard = th.zeros_like(y).scatter_(-1, y.argmax(-1, keepdim=True), 1.0)
+    c2 = _first_max_by_dst(g, (hard - y.detach() + y).flatten(1), N)
+    (c2 * w).sum().backward()
+    assert th.equal(c1, c2), "messages are exactly 0 / 1: the OR must be bit-identical"
+    assert_close(g1, logits.grad, rtol=1e-5, atol_scale=1e-6, what="grad of the encoder logits")
+    assert float(c1.sum()) > 0

@@ -34,6 +34,8 @@ _PROTOS = {
                                      _i64, _int, _int, _int, _flt, _ptr]),
     "ubs_block_mean_fwd": (C.c_int, [_F, _i64, _U, _F, _i64, _i64, _int, _int, _ptr]),
     "ubs_block_mean_bwd": (C.c_int, [_F, _i64, _U, _F, _i64, _i64, _int, _int, _ptr]),
+    "ubs_block_bitmax_fwd": (C.c_int, [_F, _i64, _F, _U, _I, _F, _i64, _ptr, _i64, _int, _int, _flt, _ptr]),
+    "ubs_block_bitmax_bwd": (C.c_int, [_F, _i64, _F, _U, _I, _ptr, _F, _i64, _F, _i64, _i64, _int, _int, _flt, _ptr]),
     "ubs_gru_gates_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gru_gates_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i64, _int, _ptr]),
     "ubs_gatv2_seg_fwd": (C.c_int, [_F] * 14 + [_i64] * 8 + [_int] * 4 + [_flt, _int, _ptr]),

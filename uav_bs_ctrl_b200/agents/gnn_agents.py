@@ -267,20 +267,28 @@ class DiscreteComm(nn.Module):
 
     def forward(self, g, x, h):
         n, M = x.shape[0], self._msg_size
-        if g.number_of_edges() == 0:
+        E = g.number_of_edges()
+        if E == 0:
             c = th.zeros(n, 2 * M, device=x.device)
         else:
-            src, _ = g.edges()
-            logits = self.f_enc(th.cat((x, h.detach()), 1)).index_select(0, src).view(-1, M, 2)
+            logits_n = self.f_enc(th.cat((x, h.detach()), 1))                  # per source NODE (N, 2M)
             if self.exponential_feed is not None:
-                e = next(self.exponential_feed).to(logits.dtype)
+                e = next(self.exponential_feed).to(logits_n.dtype)
             else:
-                e = th.empty_like(logits).exponential_()
-            # F.gumbel_softmax(logits, tau=0.5, hard=True) with the noise made explicit (straight-through one-hot)
-            y_soft = ((logits - e.log()) / 0.5).softmax(-1)
-            y_hard = th.zeros_like(y_soft).scatter_(-1, y_soft.argmax(-1, keepdim=True), 1.0)
-            m = (y_hard - y_soft.detach() + y_soft).flatten(1)
-            c = _first_max_by_dst(g, m, n)
+                e = th.empty(E, M, 2, dtype=logits_n.dtype, device=x.device).exponential_()
+            blk = g.block_mask() if x.is_cuda else None
+            if blk is not None:
+                # batched per-env comm graphs: fused kernel (noise per edge, max over the destination's bit mask)
+                block, mask = blk
+                c = ops.BlockBitMax.apply(logits_n, e.reshape(E, M, 2), mask, block, 0.5)
+            else:
+                src, _ = g.edges()
+                logits = logits_n.index_select(0, src).view(-1, M, 2)
+                # F.gumbel_softmax(logits, tau=0.5, hard=True) with the noise made explicit (straight-through one-hot)
+                y_soft = ((logits - e.log()) / 0.5).softmax(-1)
+                y_hard = th.zeros_like(y_soft).scatter_(-1, y_soft.argmax(-1, keepdim=True), 1.0)
+                m = (y_hard - y_soft.detach() + y_soft).flatten(1)
+                c = _first_max_by_dst(g, m, n)
         return self.f_udt(th.cat((x, self.f_dec(c)), 1), h)
 
 

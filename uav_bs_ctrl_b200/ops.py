@@ -269,6 +269,54 @@ class BlockMean(th.autograd.Function):
         return g, None, None
 
 
+class BlockBitMax(th.autograd.Function):
+    """DiscreteComm's per-edge hard Gumbel-softmax + element-wise max over in-edges on a block-diagonal comm graph
+    (``ubs_block_bitmax_fwd / bwd``).  ``logits (N, 2M)`` = ``f_enc`` per node, ``expo (E, M, 2)`` Exponential(1) noise in
+    edge-id order, ``mask (N,)`` int32 bit patterns, ``block`` agents per env -> ``c (N, 2M)``."""
+
+    @staticmethod
+    def forward(ctx, logits, expo, mask, block, tau):
+        _lib.require_cuda(logits, expo, mask)
+        lib = _lib.load()
+        logits, expo = _f32c(logits), _f32c(expo)
+        N, F2 = logits.shape
+        M = F2 // 2
+        if mask.dtype not in (th.int32, th.uint32) or mask.numel() != N:
+            raise TypeError("mask must be int32 (bit pattern of uint32) with one entry per node")
+        # first edge id of every env: exclusive prefix sum of the envs' edge counts (popcount of their masks)
+        m64 = mask.to(th.int64) & 0xFFFFFFFF
+        cnt = th.zeros_like(m64)
+        for i in range(block):
+            cnt += (m64 >> i) & 1
+        per_env = cnt.view(-1, block).sum(1)
+        eoff = (th.cumsum(per_env, 0) - per_env).contiguous()
+        out = th.empty(N, F2, dtype=th.float32, device=logits.device)
+        need = logits.requires_grad
+        winner = th.empty(N, F2, dtype=th.uint8, device=logits.device) if need else None
+        with _timed("block_bitmax_fwd", (N, block, M)):
+            _lib.check(lib.ubs_block_bitmax_fwd(logits.data_ptr(), F2, expo.data_ptr(), _lib.ptr(mask), eoff.data_ptr(),
+                                                out.data_ptr(), F2, _lib.ptr(winner), N, block, M, float(tau), _lib.stream()),
+                       "ubs_block_bitmax_fwd")
+        if need:
+            ctx.save_for_backward(logits, expo, mask, eoff, winner)
+            ctx.cfg = (block, M, float(tau))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, expo, mask, eoff, winner = ctx.saved_tensors
+        block, M, tau = ctx.cfg
+        lib = _lib.load()
+        grad_out = _f32c(grad_out)
+        N, F2 = logits.shape
+        g = th.empty_like(logits)
+        with _timed("block_bitmax_bwd", (N, block, M)):
+            _lib.check(lib.ubs_block_bitmax_bwd(logits.data_ptr(), F2, expo.data_ptr(), _lib.ptr(mask), eoff.data_ptr(),
+                                                winner.data_ptr(), grad_out.data_ptr(), F2, g.data_ptr(), F2, N, block, M,
+                                                tau, _lib.stream()), "ubs_block_bitmax_bwd")
+        return g, None, None, None, None
+
+
 class GRUGates(th.autograd.Function):
     """``nn.GRUCell`` gate math on precomputed projections ``gi (N,3H)``, ``gh (N,3H)`` and ``h (N,H)``."""
 

@@ -41,12 +41,39 @@ import torch as th  # noqa: E402
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
 U, G, H, HEADS, M, K, N_ACT = 8, 80, 64, 4, 64, 16, 9
 OBS_SHAPE = {"agent": 2, "ubs": 2, "gt": 4}
+FLAT, N_LAYERS, CONFIG = 0, 2, "exp3"
+
+# BASELINE.json configs[1..3].  `exp3` is the headline (the default; what the driver runs); the others are extra runs
+# (`--config`) whose lines carry their own `config.workload`.
+CONFIGS = {
+    "exp3": dict(U=8, G=80, H=64, envs=256, T=50, flat=False,
+                 name="exp3 MADRQN gnn obs + TarMAC comm"),
+    "exp2": dict(U=8, G=80, H=64, envs=256, T=50, flat=True,
+                 name="exp2 MADRQN mlp obs (flattened, 423-d) + TarMAC comm"),
+    "scaled": dict(U=16, G=320, H=128, envs=128, T=50, flat=False,
+                   name="exp3 scaled MADRQN gnn obs + TarMAC comm (1024 envs over 8 GPUs = 128 per GPU)"),
+}
+
+
+def apply_config(name, a):
+    """Sets the module-level workload shape from ``--config`` (explicit --envs / --T still win)."""
+    global U, G, H, OBS_SHAPE, FLAT, CONFIG, N_ACT
+    c = CONFIGS[name]
+    U, G, H, CONFIG = c["U"], c["G"], c["H"], name
+    FLAT = 2 + 5 * G + 3 * (U - 1) if c["flat"] else 0          # FlattenedObservation size (env_wrappers.py:41-54)
+    OBS_SHAPE = FLAT if FLAT else {"agent": 2, "ubs": 2, "gt": 4}
+    if a.envs is None:
+        a.envs = c["envs"]
+    if a.T is None:
+        a.T = c["T"]
+    return c["name"]
 
 
 def model_args(device, T, n_envs):
     """exp3 model / optimiser settings: ``algos/madrqn/config.py`` defaults + ``run_exp3.py:30-54`` overrides, with
     hidden_size=64 as BASELINE.json names it."""
-    return SimpleNamespace(device=str(device), o="gnn", c="tarmac", share_reward=False, hidden_size=H, n_layers=2,
+    return SimpleNamespace(device=str(device), o="mlp" if FLAT else "gnn", c="tarmac", share_reward=False, hidden_size=H,
+                           n_layers=N_LAYERS,
                            n_heads=HEADS, msg_size=M, key_size=K, n_rounds=1, lr=2.5e-4, gamma=0.99, polyak=0.999,
                            batch_size=1, replay_size=2, max_seq_len=T, anneal_lr=False, double_q=True, dueling=False,
                            mixer=False, n_envs=n_envs)
@@ -56,7 +83,14 @@ def make_episode(B, T, profile, seed):
     """T+1 host-resident batched observation graphs + rewards / dones, seeded (SURVEY §8(d) distributions)."""
     from uav_bs_ctrl_b200.builder import build_obs_graph_batch
     from uav_bs_ctrl_b200.synth import synth_dense_obs
-    graphs = [build_obs_graph_batch(*synth_dense_obs(B, U, G, profile, seed=seed + t)) for t in range(T + 1)]
+    graphs = []
+    for t in range(T + 1):
+        a, gt, ubs, adj = synth_dense_obs(B, U, G, profile, seed=seed + t)
+        if FLAT:                                    # exp2: flattened local observations on the comm graph
+            flat = th.cat((a.reshape(B, U, -1), gt.reshape(B, U, -1), ubs.reshape(B, U, -1)), 2)
+            graphs.append(build_obs_graph_batch(flat, th.zeros(B, U, 0, 5), th.zeros(B, U, 0, 3), adj))
+        else:
+            graphs.append(build_obs_graph_batch(a, gt, ubs, adj))
     gen = th.Generator().manual_seed(seed + 7919)
     rews = th.rand(T, B, U, generator=gen)
     dones = th.zeros(T, B)
@@ -161,14 +195,17 @@ def train_cycle_arena(learner, arena, packets, T, eps, host_io, acts_host=None):
 def make_packets(B, T, profile, seed, pin):
     from uav_bs_ctrl_b200.arena import PacketLayout, ObsPacket
     from uav_bs_ctrl_b200.synth import synth_dense_obs
-    L = PacketLayout(B, U, G)
+    L = PacketLayout(B, U, G, flat_dim=FLAT)
     gen = th.Generator().manual_seed(seed + 7919)
     out = []
     for t in range(T + 1):
         a, gt, ubs, adj = synth_dense_obs(B, U, G, profile, seed=seed + t)
         done = th.ones(B) if t == T else th.zeros(B)       # episode_limit reached on the last step (bad_mask mutes it)
-        out.append(ObsPacket(L, pin=pin).fill_from_dense(a, gt, ubs, adj, rew=th.rand(B, U, generator=gen),
-                                                         done=done, bad=done))
+        pk = ObsPacket(L, pin=pin).fill_from_dense(a, gt, ubs, adj, rew=th.rand(B, U, generator=gen), done=done, bad=done)
+        if FLAT:                                           # exp2: the MLP encoder reads flattened local observations
+            flat = th.cat((a.reshape(B * U, -1), gt.reshape(B * U, -1), ubs.reshape(B * U, -1)), 1)   # agent | gt | ubs
+            pk.sec("x_flat").view(B * U, L.flat_ld)[:, :FLAT] = flat
+        out.append(pk)
     return L, out
 
 
@@ -282,6 +319,25 @@ def run_ours(a):
     ms, launches, clocks = timed(value_step, a.steps, a.warmup, sample_clocks=True)
     value = world * B * T * a.steps / (ms * 1e-3)
 
+    # ---- strong scaling (extra leg, N > 1): the SAME total number of envs split over the ranks (256 ->
+    # 256 / N per GPU); `value` above stays the weak-scaling number the driver computes its efficiency from
+    strong = None
+    if world > 1 and use_arena and not a.no_strong and B % world == 0 and B // world >= 2:
+        Bs = B // world
+        th.manual_seed(0)
+        learner_s = MultiAgentQLearner(dict(obs_shape=OBS_SHAPE, state_shape=None, n_actions=N_ACT, n_agents=U,
+                                            episode_limit=T), model_args(dev, T, Bs))
+        learner_s.args.cuda_graphs = not a.no_graphs
+        learner_s.args.per_step_graphs = a.per_step_graphs
+        _, packets_s = make_packets(Bs, T, a.profile, seed=4321 + 100 * rank, pin=False)
+        arena_s = learner_s.new_arena(G)
+        for t in range(T + 1):
+            arena_s.load(t, packets_s[t])
+        ms_s, _, _ = timed(lambda: train_cycle_arena(learner_s, arena_s, None, T, eps, False), a.steps, a.warmup)
+        strong = {"value": B * T * a.steps / (ms_s * 1e-3), "unit": UNIT, "scaling": "strong", "total_envs": B,
+                  "envs_per_gpu": Bs, "ms_per_step": ms_s / a.steps}
+        del learner_s, arena_s, packets_s
+
     # ---- e2e: pinned host observations in, actions / loss / q-values out, every step
     e2e = None
     if not a.no_e2e:
@@ -299,7 +355,7 @@ def run_ours(a):
     # ---- full loop: the device-resident env (ubs_env_step) closes the loop — reset, T x (act -> env.step), update, with
     # nothing returning to the host; initial layouts come from the RNG-matched host sampler, drawn ahead of time
     full = None
-    if use_arena and not a.no_full:
+    if use_arena and not a.no_full and not FLAT:
         from uav_bs_ctrl_b200 import envs as E
         m = E.DenseHotSpot(n_ubs=U, n_grps=G // 5, gts_per_grp=5, episode_limit=T)
         env = E.MultiUbsCoverageVecEnv(n_envs=B, device=dev, map=m)
@@ -395,24 +451,29 @@ def run_ours(a):
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
             (6650.0, "fallback (B200_PROFILING.md)")
         nbytes, nflops = algorithmic_cost(dom, meta)
-        traffic = None
+        # DRAM bytes per launch of the dominant kernel: NOT measured in this run (that needs a profiler) — the value of
+        # the committed `ncu --set full` capture of the same kernel and shape (profiles/traffic.json), labelled as such
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{dom}{list(meta[:2])}")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{dom}{list(meta[:2])}")
+            traffic_src = f"static: {tj.get('_source', 'profiles/traffic.json')}" if traffic is not None else None
         except (OSError, ValueError):
             pass
         avg_s = tot_ms * 1e-3 / cnt
         achieved = nbytes / avg_s / 1e9
         fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else 74.5
         roofline = {"bound": "hbm", "kernel": dom, "shape": str(meta), "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "launches_timed": cnt, "avg_launch_us": 1e6 * avg_s, "algorithmic_bytes_per_launch": nbytes,
                     "algorithmic_flops_per_launch": nflops,
                     "fp32": {"achieved_tflops": nflops / avg_s / 1e12, "peak_tflops": fp32_peak,
                              "frac": nflops / avg_s / 1e12 / fp32_peak,
                              "note": "these kernels are FP32-issue bound (arithmetic intensity far right of the ridge); "
                                      "the HBM fraction is reported because the contract asks for it"},
-                    "timing": "CUDA events around each C-ABI call of one extra step (eager launches queued behind a spin "
-                              "kernel so the device runs them back to back) after the timed region",
+                    "timing": "CUDA events around each C-ABI call of one extra EAGER step (launches queued behind a spin "
+                              "kernel so the device runs them back to back) after the timed region; inside the timed "
+                              "region the act kernels are CUDA-graph nodes: their in-graph time is phases.act_ms / T",
                     "kernel_ms_per_step": {k: round(v[1], 4) for k, v in by_name.items()},
                     "kernel_calls_per_step": {k: v[0] for k, v in by_name.items()},
                     "groups_ms": {f"{k[0]}{list(k[1][:2])}": round(v[1], 4) for k, v in groups.items()},
@@ -431,14 +492,15 @@ def run_ours(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, "
-                                       f"{B} envs/GPU, T={T}, degree profile '{a.profile}'",
+                "config": {"workload": f"{a.workload_name}, {U} UBS x {G} GT, hidden={H}, "
+                                       f"{B} envs/GPU, T={T}, degree profile '{a.profile}'", "name": CONFIG,
                            "env_steps_per_step": world * B * T, "update_batch": f"{B} sequences x {T} per GPU",
                            "parallelism": f"dp{world}", "path": a.path + ("" if a.no_graphs or a.path != "arena" else
                                              "+cudagraphs(per step)" if a.per_step_graphs else "+cudagraph(act window)"),
                            "l2_policy": "inputs exceed L2: "
                            f"{h2d / 2**20:.0f} MiB of observations are streamed per step (> 126 MB L2)"},
                 "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "e2e": e2e, "full_loop": full,
+                "strong_scaling": strong,
                 "clocks": clocks,
                 "gpu_launches": int(launches)}
         print(json.dumps(line), flush=True)
@@ -530,7 +592,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * cpu["seconds"] / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"exp3 MADRQN gnn obs + TarMAC comm, {U} UBS x {G} GT, hidden={H}, {B} envs, "
+            "config": {"workload": f"{a.workload_name}, {U} UBS x {G} GT, hidden={H}, {B} envs, "
                                    f"T={T}, degree profile '{a.profile}'",
                        "env_steps_per_step": B * T,
                        "note": "reference's DGL-on-CPU path restated op-for-op in PyTorch (DGL 0.9.0 not installable)"},
@@ -545,8 +607,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=256, help="parallel env instances per GPU")
-    ap.add_argument("--T", type=int, default=50, help="sequence length = episode_limit of the exp3 maps")
+    ap.add_argument("--config", default="exp3", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the headline)")
+    ap.add_argument("--envs", type=int, default=None, help="parallel env instances per GPU (default: the config's)")
+    ap.add_argument("--T", type=int, default=None, help="sequence length = episode_limit (default: the config's, 50)")
     ap.add_argument("--cpu-T", dest="cpu_T", type=int, default=50,
                     help="sequence length of the cpu_baseline leg (default: the full T; its sample is bounded by running 1 + 2 cycles)")
     ap.add_argument("--profile", default="full", choices=["full", "realistic", "random"])
@@ -559,7 +622,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full-loop leg (device env in the loop)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling extra leg of multi-GPU runs")
     a = ap.parse_args()
+    a.workload_name = apply_config(a.config, a)
     if a.impl == "reference":
         run_reference(a)
     else:

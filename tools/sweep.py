@@ -28,6 +28,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--big", action="store_true", help="only points whose gathered rows exceed the 126 MB L2 (n = 1 M)")
+    ap.add_argument("--once", action="store_true", help="one forward + backward per point (for an outer ncu capture)")
     a = ap.parse_args()
     dev = th.device("cuda:0")
     peak = 6541.1
@@ -35,9 +37,11 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except (OSError, KeyError):
         pass
-    ns = [1000, 16000] if a.quick else [1000, 4000, 16000, 64000]
+    ns = [1000, 16000] if a.quick else [1000, 4000, 16000, 64000, 1000000]
     degs = [4, 64] if a.quick else [4, 16, 64]
     Hs = [64, 256] if a.quick else [32, 64, 128, 256]
+    if a.big:
+        ns, degs, Hs = [1000000], [4, 16], [64, 128]
     heads = 4
     flush = th.empty(256 * 1024 * 1024 // 4, dtype=th.float32, device=dev)
     rows = []
@@ -50,6 +54,8 @@ def main():
             g = G.heterograph({("s", "e", "d"): (src, dst)}, num_nodes_dict={"s": n, "d": n})
             gd = g.to(dev)
             for H in Hs:
+                if n * deg * H * 4 > 24e9:                 # keep the gathered volume of a point under 24 GB
+                    continue
                 th.manual_seed(0)
                 conv = A.GATv2Conv((H, H), H // heads, heads, residual=True, allow_zero_in_degree=True,
                                    activation=nn.ReLU()).to(dev)
@@ -61,6 +67,10 @@ def main():
                     o = conv(gd["e"], (xs, xd))
                     th.autograd.grad(o, [xs, xd] + list(conv.parameters()), go)
 
+                if a.once:
+                    step()
+                    th.cuda.synchronize()
+                    continue
                 for _ in range(2):
                     step()
                 th.cuda.synchronize()
@@ -85,7 +95,9 @@ def main():
                        "fwd_GBps": round(fb / f_us / 1e3, 1), "bwd_GBps": round(bb / b_us / 1e3, 1),
                        "fwd_frac_of_measured_hbm": round(fb / f_us / 1e3 / peak, 4),
                        "bwd_frac_of_measured_hbm": round(bb / b_us / 1e3 / peak, 4),
-                       "module_fwd_bwd_us": round(1e3 * tot / reps, 1)}
+                       "module_fwd_bwd_us": round(1e3 * tot / reps, 1),
+                       "el_MB": round(n * H * 4 / 1e6, 1), "beyond_L2": n * H * 4 > 126e6,
+                       "projection_us": {k: round(1e3 * v["ms"] / reps, 1) for k, v in summ.items() if k.startswith("tf32x3")}}
                 if a.cpu and n <= 16000:
                     from oracle import gnn_oracle as O
                     ref = O.GATv2Conv((H, H), H // heads, heads, residual=True, allow_zero_in_degree=True,

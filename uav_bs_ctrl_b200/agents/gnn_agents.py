@@ -89,15 +89,16 @@ class GATv2Conv(nn.Module):
         flags |= ops.GAT_RESIDUAL if has_res else 0
         if not ops.gatv2_fused_supported(self._in_src_feats, self._in_dst_feats, self._num_heads, self._out_feats,
                                          self._negative_slope):
-            # wide inputs (synthetic sweep): dense projections by library GEMMs, then ONE gather/softmax/aggregate pass
+            # wide inputs (synthetic sweep): dense projections on the tensor cores, then ONE gather/softmax/aggregate pass
             if not ops.gat_aggregate_supported(self._num_heads, self._out_feats, self._negative_slope):
                 raise NotImplementedError(
                     f"GATv2Conv shape (F_src={self._in_src_feats}, F_dst={self._in_dst_feats}, "
                     f"heads={self._num_heads}, D={self._out_feats}) is outside the kernels' range")
-            el = F.linear(h_src, self.fc_src.weight, self.fc_src.bias)
-            er = F.linear(h_dst, self.fc_dst.weight, self.fc_dst.bias)
+            # dense per-relation feature projections: tcgen05 3xTF32 GEMMs (ubs_tf32x3_gemm / _tn) with autograd
+            el = ops.linear(h_src, self.fc_src.weight, self.fc_src.bias)
+            er = ops.linear(h_dst, self.fc_dst.weight, self.fc_dst.bias)
             if has_res:
-                rs = F.linear(h_dst, self.res_fc.weight, self.res_fc.bias)
+                rs = ops.linear(h_dst, self.res_fc.weight, self.res_fc.bias)
             elif isinstance(self.res_fc, nn.Identity):
                 rs = h_dst.repeat(1, self._num_heads)
             else:

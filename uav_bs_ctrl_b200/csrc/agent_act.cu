@@ -24,8 +24,15 @@
 
 namespace ubs {
 namespace act {
+#ifdef UBS_ACT_TRACE
+__device__ long long ubs_act_trace[16];
+#define ATR(slot) do { if (blockIdx.x == 5 && threadIdx.x == 0) ubs_act_trace[slot] = clock64(); } while (0)
+#else
+#define ATR(slot) do { } while (0)
+#endif
 
 constexpr int NT = 512;
+constexpr int RP = 24;     // row stride of the feature-major activation tiles in THIS kernel: conflict-free mma A fragments
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -209,65 +216,85 @@ __device__ __forceinline__ void gat_rel_heads(int heads, const float* xs, int be
     }
 }
 
-// out[j*RP + r] = act(bias[j] + sum_k W[k*ldw + j] * A[k*RP + r]);  W, bias, A in shared memory.  mode 0 store, 1 relu.
-__device__ __noinline__ void gemm_s(const float* W, int ldw, const float* bias, const float* A, int Kd, float* out,
-                                       int Nout, int mode, float* scratch, int scratch_cap) {
-    const int ntc = Nout >> 2, tiles = ntc * 4;
-    int ksplit = 1;                                    // split K while threads and partial-sum scratch allow
-    while (ksplit < 8 && tiles * ksplit * 2 <= NT && Kd >= ksplit * 16 && (2 * ksplit - 1) * tiles * 16 <= scratch_cap) ksplit *= 2;
-    const int kchunk = (((Kd + ksplit - 1) / ksplit) + 3) & ~3;
-    for (int base = 0; base < tiles * ksplit; base += NT) {
-        const int t = base + threadIdx.x;
-        const bool active = t < tiles * ksplit;
-        const int ks = active ? t / tiles : 0, tile = active ? t - ks * tiles : 0;
-        const int ct = tile % ntc, rt = tile / ntc;
-        float acc[4][4];
+// ---------------------------------------------------------------------------------------------- tensor-core layers
+// Every dense layer of the step is a 16-row product: exactly the M of one mma.sync.m16n8k8 tile.  fp32 accuracy through
+// the 3xTF32 split (hi = top 11 significand bits, lo = the rest; hi.hi + hi.lo + lo.hi, fp32 accumulate), done on the
+// fly in registers.  Weights arrive in FRAGMENT ORDER (PackLayout f_*): the B operand of an MMA is one 8-byte shared
+// load per lane, conflict free; activations stay feature-major with a row stride of 24 floats, which makes the
+// A-fragment loads conflict free as well ((k0 + c) * 24 + g hits 32 different banks).  Column tile j goes to warp
+// j mod 16; a warp keeps the accumulators of its (<= MAXT) tiles in registers and alternates two accumulator sets
+// between even and odd k-steps so that no two MMAs in flight depend on each other.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
+}
+__device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// out[n * RP + r] = act(bias[n] + sum_k A[k * RP + r] W[k][n]),  n < 8 * ntiles.  All threads call; ends with __syncthreads().
+template <int MAXT>
+__device__ __forceinline__ void layer_mma(const float* Wf, const float* bias, const float* A, int Kd, float* out, int ntiles,
+                                          bool relu) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    float acc[MAXT][2][3][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-        if (active) {
-            const int k0 = ks * kchunk, k1 = min(Kd, k0 + kchunk);
-            const float* wp = W + 4 * ct;
-            const float* ap = A + 4 * rt;
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
-                const float4 x = *reinterpret_cast<const float4*>(ap + k * RP);
-                acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
-                acc[0][2] = fmaf(x.x, w.z, acc[0][2]); acc[0][3] = fmaf(x.x, w.w, acc[0][3]);
-                acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
-                acc[1][2] = fmaf(x.y, w.z, acc[1][2]); acc[1][3] = fmaf(x.y, w.w, acc[1][3]);
-                acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
-                acc[2][2] = fmaf(x.z, w.z, acc[2][2]); acc[2][3] = fmaf(x.z, w.w, acc[2][3]);
-                acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
-                acc[3][2] = fmaf(x.w, w.z, acc[3][2]); acc[3][3] = fmaf(x.w, w.w, acc[3][3]);
-            }
-        }
-        if (ksplit > 1) {
-            if (active && ks > 0) {
-                float4* sp = reinterpret_cast<float4*>(scratch + ((ks - 1) * tiles + tile) * 16);
+    for (int t = 0; t < MAXT; ++t)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) sp[r] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-            }
-            __syncthreads();
-            if (active && ks == 0) {
-                for (int s = 1; s < ksplit; ++s) {
-                    const float4* sp = reinterpret_cast<const float4*>(scratch + ((s - 1) * tiles + tile) * 16);
+        for (int s_ = 0; s_ < 2; ++s_)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float4 v = sp[r];
-                        acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[t][s_][m][q] = 0.f;
+    if (warp < ntiles) {
+        const float* ap = A + c * RP + g;
+        const float2* wp = reinterpret_cast<const float2*>(Wf) + warp * 32 + lane;
+        const int nks = Kd >> 3;
+        for (int ks = 0; ks < nks; ks += 2) {
+#pragma unroll
+            for (int s_ = 0; s_ < 2; ++s_) {
+                if (ks + s_ < nks) {
+                    const float* a0 = ap + (ks + s_) * 8 * RP;
+                    uint32_t ah[4], al[4];
+                    split_tf32(a0[0], ah[0], al[0]);
+                    split_tf32(a0[8], ah[1], al[1]);
+                    split_tf32(a0[4 * RP], ah[2], al[2]);
+                    split_tf32(a0[4 * RP + 8], ah[3], al[3]);
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        if (warp + 16 * t < ntiles) {
+                            const float2 w = wp[((ks + s_) * ntiles + 16 * t) * 32];
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(w.x, bh0, bl0);
+                            split_tf32(w.y, bh1, bl1);
+                            mma8(acc[t][s_][1], al, bh0, bh1);
+                            mma8(acc[t][s_][2], ah, bl0, bl1);
+                            mma8(acc[t][s_][0], ah, bh0, bh1);
+                        }
                     }
                 }
             }
         }
-        if (active && ks == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = 4 * ct + c;
-                const float b = bias[j];
-                float4 v = make_float4(acc[0][c] + b, acc[1][c] + b, acc[2][c] + b, acc[3][c] + b);
-                if (mode == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                *reinterpret_cast<float4*>(out + j * RP + 4 * rt) = v;
+        for (int t = 0; t < MAXT; ++t) {
+            if (warp + 16 * t < ntiles) {
+                const int n0 = 8 * (warp + 16 * t) + 2 * c;
+                const float b0 = bias[n0], b1 = bias[n0 + 1];
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    v[q] = (acc[t][0][0][q] + acc[t][1][0][q]) + ((acc[t][0][1][q] + acc[t][1][1][q]) + (acc[t][0][2][q] + acc[t][1][2][q])) +
+                           ((q & 1) ? b1 : b0);
+                if (relu) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
+                }
+                out[n0 * RP + g] = v[0];
+                out[(n0 + 1) * RP + g] = v[1];
+                out[n0 * RP + g + 8] = v[2];
+                out[(n0 + 1) * RP + g + 8] = v[3];
             }
         }
     }
@@ -303,11 +330,12 @@ __host__ __device__ inline Plan make_plan(const StepDims& d) {
     Plan p{};
     int L = 0;
     auto pad4 = [](int n) { return (n + 3) & ~3; };
-    if (d.aggr()) p.layer[L++] = Layer{P.t_aggr, pad4(d.Fin * d.H) + pad4(d.H)};
-    if (d.tarmac()) p.layer[L++] = Layer{P.t_vsq, pad4(2 * d.H * d.Vp()) + pad4(d.Vp())};
-    p.layer[L++] = Layer{P.t_ih, pad4(d.Iih() * 3 * d.H) + pad4(3 * d.H)};
-    p.layer[L++] = Layer{P.t_hh, pad4(d.H * 3 * d.H) + pad4(3 * d.H)};
-    p.layer[L++] = Layer{P.t_out, pad4(d.H * d.Ap()) + pad4(d.Ap())};
+    // fragment-order weight blocks, each followed by its bias
+    if (d.aggr()) p.layer[L++] = Layer{P.f_aggr, pad4(d.Fin * d.H) + pad4(d.H)};
+    if (d.tarmac()) p.layer[L++] = Layer{P.f_vsq, pad4(2 * d.H * d.Vp()) + pad4(d.Vp())};
+    p.layer[L++] = Layer{P.f_ih, pad4(d.Iih() * 3 * d.H) + pad4(3 * d.H)};
+    p.layer[L++] = Layer{P.f_hh, pad4(d.H * 3 * d.H) + pad4(3 * d.H)};
+    p.layer[L++] = Layer{P.f_out, pad4(d.H * d.Ap8()) + pad4(d.Ap8())};
     p.L = L;
     for (int i = 0; i < L; ++i) {
         int& cap = (i & 1) ? p.capB : p.capA;
@@ -316,9 +344,8 @@ __host__ __device__ inline Plan make_plan(const StepDims& d) {
     // activation rows: [c | x | hp] contiguous, vsq, gi, gh (aliases xin), hn, q, alpha
     const int H = d.H, H3 = 3 * H;
     const int r_xin_gh = (d.aggr() ? (d.Fin > H3 ? d.Fin : H3) : H3);
-    p.act_rows = (d.tarmac() ? d.M : 0) + H + H + (d.tarmac() ? d.Vp() : 0) + H3 + r_xin_gh + H + d.Ap() + (d.tarmac() ? d.U : 0);
-    const int budget = (227 * 1024 - 64) / 4 - p.capA - p.capB - p.act_rows * RP;
-    p.scratch = budget < NT * 16 ? (budget < 0 ? 0 : budget & ~3) : NT * 16;
+    p.act_rows = (d.tarmac() ? d.M : 0) + H + H + (d.tarmac() ? d.Vp() : 0) + H3 + r_xin_gh + H + d.Ap8() + (d.tarmac() ? d.U : 0);
+    p.scratch = 0;
     return p;
 }
 
@@ -345,7 +372,7 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
     float* sGH = take((ag ? (d.Fin > H3 ? d.Fin : H3) : H3) * RP);
     float* sXin = sGH;                                 // xin is dead once the aggregator GEMM has run
     float* sHn = take(H * RP);
-    float* sQ = take(Ap * RP);
+    float* sQ = take(d.Ap8() * RP);
     float* sAl = take(tm ? U * RP : 0);
     float* scratch = take(plan.scratch);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o);
@@ -376,6 +403,7 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
     load_tile(a.h0, row0, n_valid, H, H, sHp);
 
     for (int t = 0; t < a.T; ++t) {
+    ATR(0);
         int li = 0;                                    // index of the layer about to run
         if (fused_rel) {
             // ---- the two observation relations, staged into the (still idle) buffer of weight layer 1 ----------------
@@ -447,16 +475,19 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
             load_tile(a.xin + t * a.st_xin, row0, n_valid, d.Fin, d.Fin, ag ? sXin : sX);
         }
         __syncthreads();
+        ATR(1);
         if (ag) {
             issue(li + 1);
             wait(li);
-            gemm_s(wbuf[li & 1], H, wbuf[li & 1] + ((d.Fin * H + 3) & ~3), sXin, d.Fin, sX, H, 1, scratch, plan.scratch);
+            layer_mma<1>(wbuf[li & 1], wbuf[li & 1] + ((d.Fin * H + 3) & ~3), sXin, d.Fin, sX, H / 8, true);
             ++li;
+        ATR(2);
         }
         if (tm) {
             issue(li + 1);
             wait(li);
-            gemm_s(wbuf[li & 1], Vp, wbuf[li & 1] + ((2 * H * Vp + 3) & ~3), sX, 2 * H, sVSQ, Vp, 0, scratch, plan.scratch);
+            layer_mma<1>(wbuf[li & 1], wbuf[li & 1] + ((2 * H * Vp + 3) & ~3), sX, 2 * H, sVSQ, Vp / 8, false);
+            ATR(3);
             ++li;
             const uint32_t* mk = a.mask + t * a.st_mask;
             for (int p = threadIdx.x; p < R * U; p += NT) {
@@ -496,15 +527,18 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
                 sC[m * RP + r] = acc;
             }
             __syncthreads();
+            ATR(4);
         }
         // gi = W_ih [x ‖ c] + b_ih (smem order [c | x]),  gh = W_hh h + b_hh
         issue(li + 1);
         wait(li);
-        gemm_s(wbuf[li & 1], H3, wbuf[li & 1] + ((d.Iih() * H3 + 3) & ~3), tm ? sC : sX, d.Iih(), sGI, H3, 0, scratch, plan.scratch);
+        layer_mma<2>(wbuf[li & 1], wbuf[li & 1] + ((d.Iih() * H3 + 3) & ~3), tm ? sC : sX, d.Iih(), sGI, H3 / 8, false);
+        ATR(5);
         ++li;
         issue(li + 1);
         wait(li);
-        gemm_s(wbuf[li & 1], H3, wbuf[li & 1] + ((H * H3 + 3) & ~3), sHp, H, sGH, H3, 0, scratch, plan.scratch);
+        layer_mma<2>(wbuf[li & 1], wbuf[li & 1] + ((H * H3 + 3) & ~3), sHp, H, sGH, H3 / 8, false);
+        ATR(6);
         ++li;
         for (int p = threadIdx.x; p < H * R; p += NT) {
             const int ch = p / R, r = p - ch * R;
@@ -514,8 +548,10 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
             sHn[ch * RP + r] = fmaf(zz, sHp[ch * RP + r] - nn, nn);
         }
         __syncthreads();
+        ATR(7);
         wait(li);
-        gemm_s(wbuf[li & 1], Ap, wbuf[li & 1] + ((H * Ap + 3) & ~3), sHn, H, sQ, Ap, 0, scratch, plan.scratch);
+        layer_mma<1>(wbuf[li & 1], wbuf[li & 1] + ((H * d.Ap8() + 3) & ~3), sHn, H, sQ, d.Ap8() / 8, false);
+        ATR(8);
         if (t + 1 < a.T) issue(0);                     // every layer of this step has finished: layer 0's buffer is free
         store_tile(a.h_out + t * a.st_h, row0, n_valid, H, H, sHn);
         store_tile(a.q + t * a.st_q, row0, n_valid, A, A, sQ);
@@ -531,6 +567,7 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
         }
         for (int p = threadIdx.x; p < H * RP; p += NT) sHp[p] = sHn[p];
         __syncthreads();
+        ATR(9);
     }
 }
 
@@ -541,8 +578,9 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
 bool agent_act_fits(const StepDims& d) {
     static const bool enabled = [] { const char* e = getenv("UBS_ACT_TMA"); return !(e && e[0] == '0'); }();
     if (!enabled) return false;
+    if (!d.mma_ok() || 3 * d.H / 8 > 32 || d.H / 8 > 16 || (d.tarmac() && d.Vp() / 8 > 16)) return false;   // <= 2 column tiles per warp
     const act::Plan plan = act::make_plan(d);
-    if (act::smem_bytes(plan) > 227 * 1024 || plan.scratch < 3 * d.H * 16) return false;   // the 3H-wide GRU GEMMs need one K split
+    if (act::smem_bytes(plan) > 227 * 1024) return false;
     for (int i = 0; i < plan.L; ++i)
         if ((size_t)plan.layer[i].n * 4 >= (1u << 20)) return false;     // mbarrier tx-count range
     return true;
@@ -581,6 +619,13 @@ int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled) {
     return check_launch("ubs_agent_act_fwd(tma)");
 }
 
+#ifdef UBS_ACT_TRACE
+}  // namespace ubs
+extern "C" UBS_API int ubs_act_trace_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, ubs::act::ubs_act_trace, sizeof(long long) * 16);
+}
+namespace ubs {
+#endif
 // ---------------------------------------------------------------------------------------------- relation tables
 struct RelPackArgs {
     const float *W_src, *b_src, *W_dst, *b_dst, *attn, *W_res, *b_res;

@@ -1066,11 +1066,7 @@ extern "C" UBS_API int ubs_agent_seq2_fwd(int H, int M, int K, int U, int flags,
     // tensor-core window kernel (mma.sync 3xTF32) for the compiled (H, M, K) instances; UBS_SEQ2_MMA=0 keeps the FP32
     // kernel for A/B measurements
     if (use_mma && mma::fwd_supported(a.d) && ld_pg % 2 == 0 && ld_pv % 2 == 0) return mma::launch_fwd(a, (cudaStream_t)stream);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(seq2_fwd_kernel, "ubs_agent_seq2_fwd");
     seq2_fwd_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), NT, smem, (cudaStream_t)stream>>>(a);
     return ubs::check_launch("ubs_agent_seq2_fwd");
 }
@@ -1099,11 +1095,7 @@ extern "C" UBS_API int ubs_agent_seq2_bwd(int H, int M, int K, int U, int flags,
     if (use_mma && mma::fwd_supported(a.d) && ld_stash % 4 == 0 && ((uintptr_t)st_dgi % 16) == 0 && ((uintptr_t)st_dgh % 16) == 0 &&
         ((uintptr_t)sv_vsq % 16) == 0)
         return mma::launch_bwd(a, (cudaStream_t)stream);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(seq2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(seq2_bwd_kernel, "ubs_agent_seq2_bwd");
     seq2_bwd_kernel<<<(unsigned)((n_rows + rpt - 1) / rpt), NT, smem, (cudaStream_t)stream>>>(a);
     return ubs::check_launch("ubs_agent_seq2_bwd");
 }

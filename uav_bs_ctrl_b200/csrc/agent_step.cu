@@ -63,6 +63,26 @@ __global__ void __launch_bounds__(256) agent_pack_kernel(const PackArgs a) {
         else if (i >= L.o_ih && i < L.o_ih + H3 * I) v = a.W_ih[i - L.o_ih];
         else if (i >= L.o_hh && i < L.o_hh + H3 * H) v = a.W_hh[i - L.o_hh];
         else if (i >= L.o_out && i < L.o_out + Ap * H) { int j = i - L.o_out; v = (j / H) < A ? a.W_out[j] : 0.f; }
+        else if (i >= L.f_aggr && d.mma_ok()) {
+            // fragment-order copies: element e of lane `ln` of tile j of k-step ks = W[k = 8ks + ln%4 + 4e][n = 8j + ln/4]
+            auto frag = [&](int j_, int N, int& k, int& n) {
+                const int e = j_ & 1, ln = (j_ >> 1) & 31, tile = (j_ >> 6) % (N / 8), ks = (j_ >> 6) / (N / 8);
+                k = 8 * ks + (ln & 3) + 4 * e;
+                n = 8 * tile + (ln >> 2);
+            };
+            int k, n;
+            const int A8 = d.Ap8();
+            if (d.aggr() && i < L.f_aggr + d.Fin * H) { frag(i - L.f_aggr, H, k, n); v = a.W_aggr[n * d.Fin + k]; }
+            else if (d.aggr() && i >= L.fb_aggr && i < L.fb_aggr + H) v = a.b_aggr[i - L.fb_aggr];
+            else if (d.tarmac() && i >= L.f_vsq && i < L.f_vsq + 2 * H * Vp) { frag(i - L.f_vsq, Vp, k, n); v = vsq_w(n, k); }
+            else if (d.tarmac() && i >= L.fb_vsq && i < L.fb_vsq + Vp) v = vsq_b(i - L.fb_vsq);
+            else if (i >= L.f_ih && i < L.f_ih + I * H3) { frag(i - L.f_ih, H3, k, n); v = a.W_ih[n * I + ih_col(k)]; }
+            else if (i >= L.fb_ih && i < L.fb_ih + H3) v = a.b_ih[i - L.fb_ih];
+            else if (i >= L.f_hh && i < L.f_hh + H * H3) { frag(i - L.f_hh, H3, k, n); v = a.W_hh[n * H + k]; }
+            else if (i >= L.fb_hh && i < L.fb_hh + H3) v = a.b_hh[i - L.fb_hh];
+            else if (i >= L.f_out && i < L.f_out + H * A8) { frag(i - L.f_out, A8, k, n); v = n < A ? a.W_out[n * H + k] : 0.f; }
+            else if (i >= L.fb_out && i < L.fb_out + A8) { int c = i - L.fb_out; v = c < A ? a.b_out[c] : 0.f; }
+        }
         a.packed[i] = v;
     }
 }
@@ -543,11 +563,7 @@ extern "C" UBS_API int ubs_agent_act_fwd(int H, int M, int K, int A, int U, int 
     const unsigned grid = (unsigned)((n_rows + rpt - 1) / rpt);
     const size_t smem = (size_t)ubs::make_smem(a.d, false).total * sizeof(float);
     UBS_REQUIRE(smem <= 227 * 1024, "ubs_agent_seq_fwd: tile does not fit shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(ubs::agent_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(ubs::agent_step_fwd_kernel, "ubs_agent_seq_fwd");
     ubs::agent_step_fwd_kernel<<<grid, ubs::NT, smem, (cudaStream_t)stream>>>(a);
     return ubs::check_launch("ubs_agent_seq_fwd");
 }
@@ -573,11 +589,7 @@ extern "C" UBS_API int ubs_agent_seq_bwd(int H, int M, int K, int A, int U, int 
     const unsigned grid = (unsigned)((n_rows + rpt - 1) / rpt);
     const size_t smem = (size_t)ubs::bwd_smem_floats(a.d) * sizeof(float);
     UBS_REQUIRE(smem <= 227 * 1024, "ubs_agent_seq_bwd: tile does not fit shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(ubs::agent_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(ubs::agent_step_bwd_kernel, "ubs_agent_seq_bwd");
     ubs::agent_step_bwd_kernel<<<grid, ubs::NT, smem, (cudaStream_t)stream>>>(a);
     return ubs::check_launch("ubs_agent_seq_bwd");
 }

@@ -17,6 +17,11 @@ struct StepDims {
     __host__ __device__ bool tarmac() const { return flags & UBS_STEP_TARMAC; }
     __host__ __device__ int Iih() const { return tarmac() ? H + M : H; }    // GRU input width
     __host__ __device__ int rows_per_tile() const { return tarmac() ? (R / U) * U : R; }
+    __host__ __device__ int Ap8() const { return (A + 7) & ~7; }
+    // every contraction / output width a multiple of 8: the layers can run as mma.sync m16n8k8 tiles (agent_act.cu)
+    __host__ __device__ bool mma_ok() const {
+        return H % 8 == 0 && Fin % 8 == 0 && (!tarmac() || (M % 8 == 0 && Vp() % 8 == 0));
+    }
 };
 
 // Packed parameter buffer (floats).  "t_*" = transposed (K-major) copies for the forward GEMMs, "o_*" = original
@@ -24,6 +29,10 @@ struct StepDims {
 struct PackLayout {
     int t_aggr, b_aggr, t_vsq, b_vsq, t_ih, b_ih, t_hh, b_hh, t_out, b_out;
     int o_aggr, o_vsq, o_ih, o_hh, o_out;
+    // "f_*": the K-major matrices again in mma FRAGMENT ORDER ([k-step][8-column tile][lane][2] = W[8ks + lane%4 (+4)][8j +
+    // lane/4]: one conflict-free 8-byte shared load per B operand), each followed by a copy of its bias ("fb_*"); the Q head
+    // is padded to a multiple of 8 columns.  Present only when d.mma_ok().
+    int f_aggr, fb_aggr, f_vsq, fb_vsq, f_ih, fb_ih, f_hh, fb_hh, f_out, fb_out;
     int total;
 };
 
@@ -42,6 +51,12 @@ __host__ __device__ inline PackLayout make_layout(const StepDims& d) {
     L.o_ih = take(H3 * d.Iih());
     L.o_hh = take(H3 * H);
     L.o_out = take(d.Ap() * H);
+    const bool mm = d.mma_ok();
+    L.f_aggr = take(mm && d.aggr() ? d.Fin * H : 0);          L.fb_aggr = take(mm && d.aggr() ? H : 0);
+    L.f_vsq = take(mm && d.tarmac() ? 2 * H * d.Vp() : 0);    L.fb_vsq = take(mm && d.tarmac() ? d.Vp() : 0);
+    L.f_ih = take(mm ? d.Iih() * H3 : 0);                     L.fb_ih = take(mm ? H3 : 0);
+    L.f_hh = take(mm ? H * H3 : 0);                           L.fb_hh = take(mm ? H3 : 0);
+    L.f_out = take(mm ? H * d.Ap8() : 0);                     L.fb_out = take(mm ? d.Ap8() : 0);
     L.total = o;
     return L;
 }

@@ -51,6 +51,19 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 
 }  // namespace ubs
 
+// Kernels that need more than the 48 KB default of dynamic shared memory opt in to the device maximum ONCE per process.
+// The function-local static is initialised thread-safely (C++11), so concurrent first calls are fine and later calls
+// cost a load: no unsynchronised "configured so far" counters.
+#define UBS_OPT_IN_SMEM(kernel, what)                                                                              \
+    do {                                                                                                           \
+        static const cudaError_t ubs_rc_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                                227 * 1024);                                      \
+        if (ubs_rc_ != cudaSuccess) {                                                                              \
+            ubs::set_error("%s: cannot opt in to 227 KB of shared memory: %s", what, cudaGetErrorString(ubs_rc_)); \
+            return 1;                                                                                              \
+        }                                                                                                          \
+    } while (0)
+
 #define UBS_REQUIRE(cond, ...)            \
     do {                                  \
         if (!(cond)) {                    \

@@ -128,7 +128,8 @@ static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* s
     if (B == 0) return 0;
     StepArgs a;
     a.cfg = *cfg; a.st = *st; a.pk = *pk; a.actions = actions; a.scratch = scratch; a.B = B; a.is_reset = is_reset ? 1 : 0;
-    a.profile = getenv("UBS_ENV_PROFILE") != nullptr;
+    static const bool env_profile = getenv("UBS_ENV_PROFILE") != nullptr;      // read once per process
+    a.profile = env_profile;
     const size_t smem = Work::bytes(cfg->n_ubs, cfg->n_gts, cfg->n_rbs);
     UBS_REQUIRE(smem <= 227 * 1024, "%s: env working set (%zu B) exceeds shared memory", fn, smem);
     static size_t attr_set = 0;

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const GatArgs a) {
                         sp = fmaf(at[j], y[j], sp);
                     }
                     const float s = group_sum<LPH>(sp);
-                    const float alpha = expf(s - Mx) * invL;
+                    const float alpha = __expf(s - Mx) * invL;               // the forward's exp (same alpha in both directions)
                     float da = qk;
 #pragma unroll
                     for (int f = 0; f < FS; ++f) da = fmaf(pk[f], x[f], da);
@@ -781,11 +781,15 @@ static int launch_fwd(const GatArgs& a, int64_t n_edges, cudaStream_t st) {
     // traffic per edge); a launch that cannot fill the SMs keeps the lanes instead
     int epl = (gs < 32 || n_edges >= 64 * nd) && n_edges >= 2 * gs * nd ? 2 : 1;
     if (epl == 2 && gs > 8 && nd * (gs / 2) / 32 >= (int64_t)kNumSMs * 8 && n_edges <= 96 * nd) gs /= 2;
-    if (const char* ev = getenv("UBS_GAT_GS")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) gs = v; }
-    if (const char* ev = getenv("UBS_GAT_EPL")) { const int v = atoi(ev); if (v == 1 || v == 2) epl = v; }
+    // A/B overrides (UBS_GAT_GS / _EPL / _HS), read once per process
+    static const int env_gs = [] { const char* e = getenv("UBS_GAT_GS"); return e ? atoi(e) : 0; }();
+    static const int env_epl = [] { const char* e = getenv("UBS_GAT_EPL"); return e ? atoi(e) : 0; }();
+    static const int env_hs = [] { const char* e = getenv("UBS_GAT_HS"); return e ? atoi(e) : 0; }();
+    if (env_gs == 8 || env_gs == 16 || env_gs == 32) gs = env_gs;
+    if (env_epl == 1 || env_epl == 2) epl = env_epl;
     // head split for launches that cannot fill the SMs even with 32 lanes per destination (the act step)
     int hs = (HEADS % 2 == 0 && gs == 32 && nd < (int64_t)kNumSMs * 32) ? 2 : 1;
-    if (const char* ev = getenv("UBS_GAT_HS")) { const int v = atoi(ev); if (v == 1 || (v == 2 && HEADS % 2 == 0 && gs == 32)) hs = v; }
+    if (env_hs == 1 || (env_hs == 2 && HEADS % 2 == 0 && gs == 32)) hs = env_hs;
     const int gpb = 256 / gs;
     int64_t need = ((int64_t)a.n_dst * hs + gpb - 1) / gpb;
     int64_t cap = (int64_t)kNumSMs * 4;                            // persistent: up to 4 resident CTAs per SM

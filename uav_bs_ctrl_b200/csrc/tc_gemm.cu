@@ -555,11 +555,7 @@ extern "C" UBS_API int ubs_tf32x3_gemm(const float* A, int64_t lda, const float*
     a.A = A; a.W = W; a.bias = bias; a.C = C; a.lda = lda; a.ldw = ldw; a.ldc = ldc; a.M = M;
     a.N = N; a.K = K; a.relu = relu; a.stages = stages; a.tmem_cols = cols; a.nbuf = nbuf;
     const size_t smem = w_bytes + stages * stage_bytes + 256 + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(tf32x3_gemm_kernel, "ubs_tf32x3_gemm");
     const long long n_tiles = (M + BM - 1) / BM;
     const int grid = (int)(n_tiles < ubs::kNumSMs ? n_tiles : ubs::kNumSMs);
     tf32x3_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
@@ -598,11 +594,7 @@ extern "C" UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const flo
     while (cols < 2 * No * a.nbuf) cols *= 2;
     a.tmem_cols = cols;
     const size_t smem = stages * stage_bytes + depth * stg_bytes + 256 + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(tf32x3_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    UBS_OPT_IN_SMEM(tf32x3_gemm_tn_kernel, "ubs_tf32x3_gemm_tn");
     const int grid = (int)(a.n_items < ubs::kNumSMs ? a.n_items : ubs::kNumSMs);
     tf32x3_gemm_tn_kernel<<<grid, TN_THREADS, smem, (cudaStream_t)stream>>>(a);
     if (int rc = ubs::check_launch("ubs_tf32x3_gemm_tn")) return rc;

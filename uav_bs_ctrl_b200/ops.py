@@ -746,6 +746,36 @@ def dense(x, w, bias=None, relu=False):
     return th.relu_(out) if relu else out
 
 
+class TCLinear(th.autograd.Function):
+    """``x @ w.T + b`` with autograd, every product on the tensor cores when the shape fits (3xTF32, fp32-accurate):
+    forward and ``grad_x`` through ``ubs_tf32x3_gemm``, ``grad_w = grad.T @ x`` through ``ubs_tf32x3_gemm_tn`` — the dense
+    per-relation feature projection of wide-input GATv2 relations (the synthetic sweep).  Falls back to the fp32 library
+    GEMM per product where a shape is outside the kernels (``dense`` / ``matmul_tn`` decide)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _f32c(x), _f32c(w)
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        return dense(x, w, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32c(g)
+        gx = dense(g, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        gw = matmul_tn(g, x) if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+def linear(x, w, b=None):
+    """``F.linear`` for the wide projections: tensor cores (3xTF32) for CUDA inputs with >= 512 rows, else the library."""
+    if x.is_cuda and x.dim() == 2 and x.shape[0] >= 512 and x.dtype == th.float32:
+        return TCLinear.apply(x, w, b)
+    return th.nn.functional.linear(x, w, b)
+
+
 class Seq2Weights:
     """Derived weight tensors of the resident-weight sequence path, rebuilt only when a parameter changes:
     ``Wx (Vp+3H, H)`` = ``[W_vsq[:, :H]; W_ih[:, :H]]`` and its bias (ONE observation-side GEMM gives ``[pv | pg]``),

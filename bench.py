@@ -235,6 +235,15 @@ def algorithmic_cost(name, meta):
     if name.startswith("tf32x3"):                       # C (M,N) = A (M,K) B (K,N): fp32 in / out, 3 TF32 MMAs per product
         M_, N_, K_ = meta
         return 4 * (M_ * K_ + K_ * N_ + M_ * N_), 2 * M_ * N_ * K_
+    if name == "agent_act_rel":
+        # one-kernel act step: both star relations at capacity degree (cap rows per destination) + the agent step; the
+        # relation outputs never leave the SM, so no xin traffic
+        _, N_, ints, (F_gt, cap_gt, F_ubs, cap_ubs, heads) = meta
+        Hh, M_, K_, A_, U_, Fin, flags = ints
+        b_seen, f_seen = algorithmic_cost("gatv2_fwd", (N_, N_ * cap_gt, F_gt, 2, heads, Hh // heads, False))
+        b_near, f_near = algorithmic_cost("gatv2_fwd", (N_, N_ * cap_ubs, F_ubs, 2, heads, Hh // heads, False))
+        b_step, f_step = algorithmic_cost("agent_seq_fwd", (1, N_, ints, False))
+        return b_seen + b_near + b_step - 4 * N_ * (2 * Hh + Fin), f_seen + f_near + f_step
     T_, N_, ints, train = meta
     Hh, M_, K_, A_, U_, Fin, flags = ints
     tm = bool(flags & 2)

@@ -45,6 +45,8 @@ def main(path):
         ia, isrc = hdr.index("Instructions Executed"), hdr.index("Source")
         ops = collections.Counter()
         for r in data:
+            if len(r) <= max(ia, isrc) or not r[ia].isdigit():          # kernel-name separator rows of multi-kernel reports
+                continue
             s = re.sub(r"^@!?U?P\d+\s+", "", r[isrc].strip())
             ops[s.split()[0].split(".")[0] if s else "?"] += int(r[ia])
         tot = sum(ops.values())

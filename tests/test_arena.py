@@ -15,11 +15,33 @@ SHAPE = {'agent': 2, 'ubs': 2, 'gt': 4}
 def test_layout_sections_are_aligned_and_disjoint():
     L = PacketLayout(5, 3, 7)
     ends = 0
-    for name in ("x_gt", "x_ubs", "x_agent", "ip_seen", "ip_near", "mask", "rew", "done", "bad"):
-        assert L.off[name] % 4 == 0 and L.off[name] >= ends
+    for name in ("x_agent", "ip_seen", "ip_near", "mask", "rew", "done", "bad", "x_ubs", "x_gt"):
+        assert L.off[name] % 32 == 0 and L.off[name] >= ends          # 128-byte lines
         ends = L.off[name] + L.size[name]
-    assert L.words % 4 == 0 and L.words >= ends
+    assert L.words % 32 == 0 and L.words >= ends
     assert L.size["x_gt"] == 5 * 3 * 7 * 4 and L.size["ip_seen"] == 16
+    # the `seen` rows are the last section: a packet's live words are one prefix
+    assert L.off["x_gt"] + L.size["x_gt"] == ends and L.used_words(0) <= L.off["x_gt"] + 3
+    assert L.used_words(5 * 3 * 7) == ends <= L.words and L.used_words(10) == (L.off["x_gt"] + 40 + 3) // 4 * 4
+
+
+def test_compact_load_ships_the_live_prefix_only():
+    B, U, G, T = 4, 5, 6, 2
+    L = PacketLayout(B, U, G)
+    ar = SequenceArena(L, T, 8, "cpu")
+    ar.buf.fill_(-7)
+    pk = ObsPacket(L).fill_from_dense(*synth_dense_obs(B, U, G, "realistic", seed=3, comm_p=0.5, near_p=0.6))
+    n_seen = int(pk.sec("ip_seen")[-1])
+    assert 0 < n_seen < B * U * G
+    nbytes = ar.load(1, pk)
+    assert nbytes == 4 * L.used_words(n_seen) < 4 * L.words
+    assert th.equal(ar.buf[1, :nbytes // 4], pk.buf[:nbytes // 4]) and bool((ar.buf[1, nbytes // 4:] == -7).all())
+    g, ref = ar.graph(1), pk.to_graph()                         # the slot reads back as the same graph
+    assert th.equal(g.nodes["gt"].data["feat"], ref.nodes["gt"].data["feat"])
+    assert th.equal(g.nodes["ubs"].data["feat"], ref.nodes["ubs"].data["feat"])
+    # refilling the packet with a denser observation re-sizes the prefix
+    pk.fill_from_dense(*synth_dense_obs(B, U, G, "full", seed=3))
+    assert ar.load(0, pk) == 4 * L.used_words(B * U * G) and ar.load(0, pk, compact=False) == 4 * L.words
 
 
 @pytest.mark.parametrize("profile,comm_p", [("full", 1.0), ("realistic", 0.5), ("random", 0.3)])

@@ -75,3 +75,17 @@ def test_tf32x3_gemm_tn_strided_views():
     out = ops.tc_matmul_tn(a, x)
     ref = a.double().t() @ x.double()
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+def test_matmul_tn_pads_rows_that_are_not_16_byte_granular():
+    """dW_out: the Q head has n_actions = 9 columns; ``matmul_tn`` pads them to 12 so that the long reduction stays on the
+    kernel's vector producer path, and cuts the result back."""
+    g = th.Generator().manual_seed(5)
+    a = th.randn(8192, 9, generator=g)
+    b = th.randn(8192, 64, generator=g)
+    ops.TIMER = ops.KernelTimer()
+    out = ops.matmul_tn(a.to(DEV), b.to(DEV))
+    used = ops.TIMER.summary()
+    ops.TIMER = None
+    assert "tf32x3_gemm_tn" in used and out.shape == (9, 64)
+    assert_as_accurate(out, a.t() @ b, a.double().t() @ b.double(), what="padded gemm_tn", slack=4.0, floor_scale=2e-6)

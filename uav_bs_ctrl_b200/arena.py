@@ -41,9 +41,12 @@ class PacketLayout:
         self.F_ag, self.F_gt, self.F_ubs = F_ag, F_gt, F_ubs
         N = self.N
         self.cap_gt, self.cap_ubs = N * G, N * max(U - 1, 0)
-        sizes = [("x_gt", self.cap_gt * F_gt), ("x_ubs", self.cap_ubs * F_ubs), ("x_agent", N * F_ag),
-                 ("ip_seen", N + 1), ("ip_near", N + 1), ("mask", N), ("rew", N), ("done", B), ("bad", B)]
-        self.state_dim = state_dim                                   # global env state (QMIX), optional last section
+        # fixed-size sections first, the two CSR row stores last: a packet's live words are one prefix
+        # (``used_words``) — everything up to the last `seen` row — so staging copies the rows an observation has,
+        # not the N*G-row capacity
+        sizes = [("x_agent", N * F_ag), ("ip_seen", N + 1), ("ip_near", N + 1), ("mask", N), ("rew", N), ("done", B),
+                 ("bad", B)]
+        self.state_dim = state_dim                                   # global env state (QMIX), optional
         if state_dim:
             sizes.append(("state", B * state_dim))
         # flattened local observations for the MLP encoder (optional): rows padded to a multiple of 32 floats so that
@@ -51,18 +54,23 @@ class PacketLayout:
         self.flat_dim, self.flat_ld = flat_dim, (flat_dim + 31) // 32 * 32
         if flat_dim:
             sizes.append(("x_flat", N * self.flat_ld))
+        sizes += [("x_ubs", self.cap_ubs * F_ubs), ("x_gt", self.cap_gt * F_gt)]
         self.off: Dict[str, int] = {}
         self.size: Dict[str, int] = {}
         o = 0
         for name, n in sizes:
             self.off[name], self.size[name] = o, n
-            o += _al4(n)
+            o += (n + 31) // 32 * 32                  # every section starts on a 128-byte line (slots too: words % 32 == 0)
         self.words = o
 
     def section(self, buf: th.Tensor, name: str) -> th.Tensor:
         """Typed view of a section of ``buf`` (``(..., words)`` int32): float32 for feature / reward sections."""
         v = buf[..., self.off[name]:self.off[name] + self.size[name]]
         return v.view(th.float32) if name in self.FLOAT else v
+
+    def used_words(self, n_seen: int) -> int:
+        """Length of the live prefix of a packet whose `seen` relation has ``n_seen`` edges (16-byte granular)."""
+        return min(self.words, _al4(self.off["x_gt"] + n_seen * self.F_gt))
 
     def key(self):
         return (self.B, self.U, self.G, self.F_ag, self.F_gt, self.F_ubs, self.state_dim, self.flat_dim)
@@ -78,9 +86,22 @@ class ObsPacket:
             if pin and buf.device.type == "cpu":
                 buf = buf.pin_memory()
         self.buf = buf
+        self._used = None
 
     def sec(self, name):
         return self.layout.section(self.buf, name)
+
+    def used_words(self) -> int:
+        """Words of the live prefix (header + CSR rows in use); cached — call ``touch()`` after rewriting the packet."""
+        if self._used is None:
+            if self.buf.device.type != "cpu":
+                return self.layout.words                      # a device packet: no host read-back just to size a copy
+            self._used = self.layout.used_words(int(self.sec("ip_seen")[self.layout.N]))
+        return self._used
+
+    def touch(self):
+        self._used = None
+        return self
 
     def fill_from_dense(self, agent_obs, gt_obs, ubs_obs, comm_adj=None, rew=None, done=None, bad=None, state=None):
         """Dense env observations (``envs/mubs_cov/mubs_cov.py:215-242`` format, see ``builder.py``) → packet."""
@@ -114,6 +135,7 @@ class ObsPacket:
         self.sec("bad")[:] = 0 if bad is None else bad.reshape(-1).float()
         if L.state_dim:
             self.sec("state")[:] = 0 if state is None else state.reshape(-1).float()
+        self._used = None
         return self
 
     def to_graph(self) -> HeteroGraph:
@@ -171,9 +193,13 @@ class SequenceArena:
     def ptr(self, name, t=0) -> int:
         return self.buf.data_ptr() + 4 * (t * self.layout.words + self.layout.off[name])
 
-    def load(self, t: int, packet: ObsPacket):
-        """Stages a packet into slot t: ONE asynchronous copy (H2D when the packet is pinned host memory)."""
-        self.buf[t].copy_(packet.buf, non_blocking=True)
+    def load(self, t: int, packet: ObsPacket, compact: bool = True) -> int:
+        """Stages a packet into slot t: ONE asynchronous copy (H2D when the packet is pinned host memory) of the
+        packet's live prefix — the rows past ``ip_seen[-1]`` are never read (every kernel walks the CSR row pointers),
+        so they are not shipped.  Returns the bytes copied."""
+        n = packet.used_words() if compact else self.layout.words
+        self.buf[t, :n].copy_(packet.buf[:n], non_blocking=True)
+        return n * 4
 
     def graph(self, t: int) -> HeteroGraph:
         return packet_graph(self.layout, self.buf[t])

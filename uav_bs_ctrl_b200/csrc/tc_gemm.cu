@@ -10,12 +10,13 @@
 //
 // Structure (one CTA per SM, persistent over 128-row tiles of A; no TMA descriptors needed because the split has to
 // pass through the CUDA cores anyway):
-//   warps 0-3  producers : coalesced 16-byte global loads of the A tile chunk (128 rows x 32 floats), hi/lo split in
-//                          registers, st.shared into the canonical K-major SWIZZLE_128B layout, fence.proxy.async,
-//                          mbarrier arrive (full[stage])
-//   warp  8    MMA issuer: one thread issues 12 tcgen05.mma.kind::tf32 (M=128, N, K=8) per chunk and commits to
+//   warps 0-11 producers : three groups of 128 threads on alternate chunks (48 KB of loads in flight per SM): coalesced
+//                          16-byte global loads of the A tile chunk (128 rows x 32 floats), hi/lo split in registers,
+//                          st.shared into the canonical K-major SWIZZLE_128B layout, fence.proxy.async, mbarrier
+//                          arrive (full[stage])
+//   warp  16   MMA issuer: one thread issues 12 tcgen05.mma.kind::tf32 (M=128, N, K=8) per chunk and commits to
 //                          empty[stage] / tmem_full[acc]; this warp also owns tcgen05.alloc / dealloc
-//   warps 4-7  epilogue  : tcgen05.ld 32x32b (each warp its own TMEM lane quadrant), bias + ReLU, 64-byte row stores
+//   warps 12-15 epilogue : tcgen05.ld 32x32b (each warp its own TMEM lane quadrant), bias + ReLU, 64-byte row stores
 //   W (both halves) is split once per CTA and stays resident in shared memory; accumulators are double buffered in
 //   TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -24,7 +25,10 @@
 namespace ubs {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, NPROD = 128, NTHREADS = 288;
+// NGRP producer groups of 128 threads take alternate chunks: one group holds a 16 KB chunk in registers between its
+// loads and its stores, and 16 KB in flight per SM is far below what HBM latency x bandwidth asks for (~35 KB)
+constexpr int BM = 128, BK = 32, NPROD = 128, NGRP = 3, NTHREADS = (4 * NGRP + 5) * 32;
+constexpr int EPI_WARP0 = 4 * NGRP, MMA_WARP = 4 * NGRP + 4;          // EPI_WARP0 % 4 == 0: warp % 4 = its TMEM lane quadrant
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tf32x3_gemm_kernel(const Args a) 
         for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }   // a.nbuf of them are used
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -135,33 +139,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) tf32x3_gemm_kernel(const Args a) 
     const uint32_t tmem_base = *tmem_slot;
     const long long n_tiles = (a.M + BM - 1) / BM;
 
-    if (warp < 4) {
+    if (warp < EPI_WARP0) {
         // ================================ producers ================================
-        const int t = threadIdx.x;                                  // 0..127
+        const int grp = warp >> 2, t = threadIdx.x & 127;           // group, thread within the group
         const int c = t & 7, r0 = t >> 3;                           // chunk within the 128-byte row, first row
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long m0 = tile * BM;
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                float4 x[8];
+        const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)KC;    // chunks of this CTA, in the order the MMA warp eats them
+        // chunk `it` = (tile it / KC, kc = it % KC) lives in stage it % S; this group takes it = grp, grp + ngrp, ...
+        // No more groups than stages: a group waits for the MMAs of chunk it - S by PARITY, which is only unambiguous
+        // if that barrier cannot be two phases behind — i.e. if the group's previous chunk it - ngrp is not older than
+        // it - S (the MMAs complete in order).
+        const uint32_t ngrp = S < NGRP ? (uint32_t)S : (uint32_t)NGRP;
+        uint32_t tl = (uint32_t)grp / (uint32_t)KC, kc = (uint32_t)grp % (uint32_t)KC;
+        const uint32_t d_tl = ngrp / (uint32_t)KC, d_kc = ngrp % (uint32_t)KC;
+        for (uint32_t it = grp; (uint32_t)grp < ngrp && it < n_it; it += ngrp) {
+            const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+            const long long m0 = ((long long)blockIdx.x + (long long)tl * gridDim.x) * BM;
+            const float* src = a.A + (m0 + r0) * a.lda + (size_t)kc * BK;
+            float4 x[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                       // issue the global loads before waiting for the slot
-                    const long long row = m0 + r0 + 16 * j;
-                    x[j] = row < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + row * a.lda + (size_t)kc * BK) + c)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                mbar_wait(empty + s, ph ^ 1);
-                char* hi = sA + (size_t)s * 2 * BM * 128;
-                char* lo = hi + BM * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) split_store(hi, lo, r0 + 16 * j, c, x[j]);
-                fence_proxy_async();
-                mbar_arrive(full + s);
+            for (int j = 0; j < 8; ++j) {                           // issue the global loads before waiting for the slot
+                x[j] = m0 + r0 + 16 * j < a.M ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(16 * j) * a.lda) + c)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            mbar_wait(empty + s, ph ^ 1u);
+            char* hi = sA + (size_t)s * 2 * BM * 128;
+            char* lo = hi + BM * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_store(hi, lo, r0 + 16 * j, c, x[j]);
+            fence_proxy_async();
+            mbar_arrive(full + s);
+            tl += d_tl; kc += d_kc;
+            if (kc >= (uint32_t)KC) { kc -= (uint32_t)KC; ++tl; }
         }
-    } else if (warp == 8) {
+    } else if (warp == MMA_WARP) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -193,8 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tf32x3_gemm_kernel(const Args a) 
             }
         }
     } else {
-        // ================================ epilogue (warps 4..7) ================================
-        const int q = warp - 4;                                     // TMEM lane quadrant of this warp (warp % 4)
+        // ================================ epilogue (4 warps) ================================
+        const int q = warp - EPI_WARP0;                             // TMEM lane quadrant of this warp (warp % 4)
         uint32_t tc_ = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc_) {
             const int acc = tc_ % a.nbuf;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tf32x3_gemm_kernel(const Args a) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
     }
@@ -300,7 +311,10 @@ __device__ __forceinline__ void split_store_t(char* hi_tile, char* lo_tile, int 
     *reinterpret_cast<float*>(lo_tile + off) = l;
 }
 
-constexpr int TN_PROD_WARPS = 8, TN_THREADS = (TN_PROD_WARPS + 5) * 32;   // 8 producers | 4 epilogue | 1 MMA
+// 2 x 8 producer warps | 4 epilogue | 1 MMA.  The two producer groups take alternate chunks (one UMMA stage each): a
+// chunk costs a producer warp ~500 dependent-ish instructions, and two warps per scheduler cannot hide their latency.
+constexpr int TN_PROD_WARPS = 8, TN_GROUPS = 2, TN_EPI_WARP0 = TN_PROD_WARPS * TN_GROUPS, TN_MMA_WARP = TN_EPI_WARP0 + 4;
+constexpr int TN_THREADS = (TN_MMA_WARP + 1) * 32;
 
 // Asynchronous copy of 4 consecutive columns of one row into a private 16-byte staging slot, zero-filled outside the
 // matrix (cp.async src-size 0): the global -> shared traffic of several chunks is in flight per thread without
@@ -336,6 +350,141 @@ __device__ __forceinline__ void tn_stage(const ArgsTN& a, uint32_t stg, long lon
                           a.R, a.b_vec);
 }
 
+// Producer loop for 16-byte-aligned operands (the shapes of the BPTT window).  What a producer thread touches is fixed
+// by (warp, lane): 16 A columns (4 float4) and every 8th float4 column of B, row `lane` of every 32-row chunk.  With
+// the tile row m = warp * 16 + 4 j + e the swizzle term (m & 7) is a compile-time constant per (j, e), so the
+// K-major SWIZZLE_128B address of an element is  stage base + per-thread constant (8 of them, hoisted) + immediate:
+// ~7 instructions per element (5 to split, 2 stores) instead of re-deriving row clamps, 64-bit addresses and swizzles.
+// A columns past Mo are skipped altogether: they only feed accumulator rows the epilogue never reads.
+__device__ __forceinline__ void tn_produce_vec(const ArgsTN& a, char* sT, char* sStage, uint64_t* full, uint64_t* empty,
+                                               uint32_t stage_bytes, uint32_t b_tile, int grp, int warp, int lane) {
+    // grp: producer group (chunks grp, grp + TN_GROUPS, ...); warp: 0..7 within the group
+    constexpr int KC = SLICE / BK;
+    static_assert(KC % TN_GROUPS == 0, "a group keeps the same kc residue in every work item");
+    const int No = a.No, S = a.stages, D = a.depth;                 // D: staging slots of ONE group
+    const int nb4 = (No / 4 - warp + TN_PROD_WARPS - 1) / TN_PROD_WARPS;          // <= 4 (No <= 128)
+    const uint32_t n_items = (uint32_t)a.n_items, n_mt = (uint32_t)a.n_mtiles;
+    const uint32_t my_items = n_items > blockIdx.x ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t n_chunks = my_items * (KC / TN_GROUPS);          // chunks of this group
+    const uint32_t slots = 4 + (uint32_t)((No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS);
+    const uint32_t stg_stage = slots * TN_PROD_WARPS * 32 * 16;
+    const uint32_t tig = (uint32_t)(warp * 32 + lane);              // thread within the group
+    sStage += (size_t)grp * D * stg_stage;                          // this group's staging slots
+    const uint32_t stg0 = smem_u32(sStage) + tig * 16;
+    const uint32_t c = (uint32_t)lane >> 2, lane_off = ((uint32_t)lane & 3u) << 2;
+    uint32_t preA[8], preB[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) preA[k] = ((c ^ (uint32_t)k) << 4) + lane_off + (uint32_t)warp * 2048u;
+    const uint32_t kb0 = 4u * ((uint32_t)warp & 1u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        preB[e] = ((c ^ (kb0 + e)) << 4) + lane_off + (kb0 + e) * 128u + ((uint32_t)warp >> 1) * 1024u + 2u * BM * 128u;
+
+    // number of valid float4 A columns of this warp in m-tile mt: clamp((Mo - mt*128 - warp*16) / 4, 0, 4)
+    auto n_valid_a = [&](uint32_t mt) {
+        const int v = (a.Mo - (int)mt * BM - warp * 16) >> 2;
+        return v < 0 ? 0 : (v > 4 ? 4 : v);
+    };
+    // the staging stream (chunk g + D) and the consuming stream (chunk g) each carry their own (slot, kc, mt, slice)
+    // counters, advanced incrementally: one 32-bit division per 8 chunks instead of several per chunk
+    struct Cursor { uint32_t slot, kc, item, mt, sl; };
+    auto cursor_init = [&](Cursor& q) {
+        q.slot = 0; q.kc = (uint32_t)grp; q.item = blockIdx.x; q.sl = q.item / n_mt; q.mt = q.item - q.sl * n_mt;
+    };
+    auto cursor_next = [&](Cursor& q) {
+        q.slot = q.slot + 1 == (uint32_t)D ? 0 : q.slot + 1;
+        q.kc += TN_GROUPS;
+        if (q.kc >= KC) { q.kc -= KC; q.item += gridDim.x; q.sl = q.item / n_mt; q.mt = q.item - q.sl * n_mt; }
+    };
+    auto stage_chunk = [&](const Cursor& q) {
+        const long long row = (long long)q.sl * SLICE + q.kc * BK + lane;
+        const bool rowok = row < a.R;
+        const long long r = rowok ? row : a.R - 1;
+        const uint32_t dst = stg0 + q.slot * stg_stage;
+        const int na = n_valid_a(q.mt);
+        const float* pa = a.A + r * a.lda + (q.mt * BM + warp * 16);
+        const int sz = rowok ? 16 : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < na)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(j * TN_PROD_WARPS * 32 * 16)), "l"(pa + 4 * j), "r"(sz) : "memory");
+        const float* pb = a.B + r * a.ldb + 4 * warp;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nb4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)((4 + j) * TN_PROD_WARPS * 32 * 16)), "l"(pb + 4 * TN_PROD_WARPS * j), "r"(sz) : "memory");
+    };
+    auto split = [](float x, float& h, float& l) {
+        h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+        l = __uint_as_float((__float_as_uint(x - h) + 0x1000u) & 0xFFFFE000u);
+    };
+
+    Cursor qs, qc;                                                                   // staging / consuming
+    cursor_init(qs);
+    cursor_init(qc);
+    for (uint32_t g = 0; g < (uint32_t)D; ++g) {                                     // prologue: D chunks in flight
+        if (g < n_chunks) { stage_chunk(qs); cursor_next(qs); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (uint32_t g = 0; g < n_chunks; ++g) {
+        const uint32_t gg = g * TN_GROUPS + (uint32_t)grp;                           // position in the CTA's chunk order
+        const uint32_t s = gg % (uint32_t)S, ph = (gg / (uint32_t)S) & 1u;           // its UMMA stage and phase
+        if (D == 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
+        else if (D == 5) asm volatile("cp.async.wait_group 4;" ::: "memory");
+        else if (D == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int na = n_valid_a(qc.mt);
+        const char* stg = sStage + (size_t)qc.slot * stg_stage + (size_t)tig * 16;
+        float4 xa[4], xb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < na) xa[j] = *reinterpret_cast<const float4*>(stg + (size_t)(j * TN_PROD_WARPS * 32) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nb4) xb[j] = *reinterpret_cast<const float4*>(stg + (size_t)((4 + j) * TN_PROD_WARPS * 32) * 16);
+        if (g + (uint32_t)D < n_chunks) { stage_chunk(qs); cursor_next(qs); }       // the slot is free again: refill it
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        cursor_next(qc);
+        mbar_wait(empty + s, ph ^ 1u);
+        char* st = sT + (size_t)s * stage_bytes;                   // {A hi 16 KB | A lo 16 KB | B hi | B lo}
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < na) {
+                const float v[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int mr = 4 * j + e, k = mr & 7;           // compile-time after unrolling
+                    float h, l;
+                    split(v[e], h, l);
+                    char* p = st + preA[k] + (mr >> 3) * 1024 + k * 128;
+                    *reinterpret_cast<float*>(p) = h;
+                    *reinterpret_cast<float*>(p + BM * 128) = l;
+                }
+            }
+        }
+        char* stb_lo = st + b_tile;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nb4) {
+                const float v[4] = {xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float h, l;
+                    split(v[e], h, l);
+                    *reinterpret_cast<float*>(st + preB[e] + j * 4096) = h;          // n = 4 (warp + 8 j) + e: 4 KB per j
+                    *reinterpret_cast<float*>(stb_lo + preB[e] + j * 4096) = l;
+                }
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(full + s);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const ArgsTN a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -346,7 +495,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
     const uint32_t stage_bytes = 2 * BM * 128 + 2 * b_tile;        // {A hi, A lo, B hi, B lo}
     char* sT = smem;
     char* sStage = sT + (size_t)S * stage_bytes;                   // cp.async staging: depth x slots x 256 x 16 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + (size_t)a.depth * a.stage_stg_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + (size_t)TN_GROUPS * a.depth * a.stage_stg_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + S;
     uint64_t* tfull = bars + 2 * S;
@@ -357,7 +506,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
         for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TN_PROD_WARPS + 4) {
+    if (warp == TN_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -366,8 +515,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < TN_PROD_WARPS) {
-        // ================================ producers (transposing split) ================================
+    if (warp < TN_EPI_WARP0 && a.a_vec && a.b_vec) {
+        tn_produce_vec(a, sT, sStage, full, empty, stage_bytes, b_tile, warp / TN_PROD_WARPS, warp % TN_PROD_WARPS, lane);
+    } else if (warp < TN_PROD_WARPS) {
+        // ================================ producers (transposing split), any alignment ================================
         // warp w: 16 columns of the A tile and every 8th float4 column of the B tile; lane = row of the chunk.
         // cp.async keeps `depth` chunks in flight per thread in private staging slots (no registers held).
         const int nb4 = (No / 4 - warp + TN_PROD_WARPS - 1) / TN_PROD_WARPS;          // <= 4 (No <= 128)
@@ -430,7 +581,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
             mbar_arrive(full + s);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == TN_PROD_WARPS + 4) {
+    } else if (warp < TN_EPI_WARP0) {
+        // second producer group: idle on the any-alignment path
+    } else if (warp == TN_MMA_WARP) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(No >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -460,7 +613,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
         }
     } else {
         // ================================ epilogue (warps 8..11): partial tile -> workspace ================================
-        const int q = warp - TN_PROD_WARPS;            // == warp % 4: the TMEM lane quadrant this warp may read
+        const int q = warp - TN_EPI_WARP0;             // == warp % 4: the TMEM lane quadrant this warp may read
         uint32_t tc_ = 0;
         for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x, ++tc_) {
             const int acc = tc_ % a.nbuf;
@@ -502,31 +655,46 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TN_PROD_WARPS + 4) {
+    if (warp == TN_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
     }
 }
 
-// C[m, n] = sum over slices of ws[sl, m, n], four interleaved accumulators combined in a fixed order
-__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ ws, long long n_slices, int P, int No,
-                                                        float* __restrict__ C, long long ldc) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= P) return;
+// C[m, n] = sum over slices of ws[sl, m, n] in a fixed order.  A block owns 32 consecutive outputs; its 8 warps take
+// the slices w, w + 8, ... (16 independent loads in flight per thread, 128-byte coalesced), then the 8 partial sums are
+// added in warp order: hundreds of slices cost a few dependent load rounds instead of one thread walking all of them.
+constexpr int RED_OUT = 32, RED_WARPS = 8;
+__global__ void __launch_bounds__(RED_OUT * RED_WARPS) tn_reduce_kernel(const float* __restrict__ ws, long long n_slices, int P, int No,
+                                                                        float* __restrict__ C, long long ldc) {
+    __shared__ float part[RED_WARPS][RED_OUT];
+    const int lane = threadIdx.x % RED_OUT, w = threadIdx.x / RED_OUT;
+    const int i = blockIdx.x * RED_OUT + lane;
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    long long sl = 0;
-    for (; sl + 15 < n_slices; sl += 16) {              // 16 independent loads in flight per thread
+    if (i < P) {
+        long long sl = w;
+        for (; sl + 15 * RED_WARPS < n_slices; sl += 16 * RED_WARPS) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += ws[(sl + j) * P + i];
+            for (int j = 0; j < 16; ++j) acc[j] += ws[(sl + j * RED_WARPS) * P + i];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (sl + j * RED_WARPS < n_slices) acc[j] += ws[(sl + j * RED_WARPS) * P + i];
     }
-    for (int j = 0; sl < n_slices; ++sl, ++j) acc[j] += ws[sl * P + i];
 #pragma unroll
-    for (int w = 8; w > 0; w >>= 1)
+    for (int h = 8; h > 0; h >>= 1)
 #pragma unroll
-        for (int j = 0; j < w; ++j) acc[j] += acc[j + w];
-    C[(long long)(i / No) * ldc + (i % No)] = acc[0];
+        for (int j = 0; j < h; ++j) acc[j] += acc[j + h];
+    part[w][lane] = acc[0];
+    __syncthreads();
+    if (w == 0 && i < P) {
+        float t = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < RED_WARPS; ++k) t += part[k][lane];
+        C[(long long)(i / No) * ldc + (i % No)] = t;
+    }
 }
 
 }  // namespace tc
@@ -578,6 +746,8 @@ extern "C" UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const flo
     a.A = A; a.B = B; a.ws = workspace; a.lda = lda; a.ldb = ldb; a.R = R; a.Mo = Mo; a.No = No;
     a.a_vec = (lda % 4 == 0 && Mo % 4 == 0 && ((uintptr_t)A % 16) == 0) ? 1 : 0;
     a.b_vec = (ldb % 4 == 0 && ((uintptr_t)B % 16) == 0) ? 1 : 0;
+    static const bool generic = [] { const char* e = getenv("UBS_TN_GENERIC"); return e && e[0] == '1'; }();   // debugging: any-alignment path
+    if (generic) a.a_vec = a.b_vec = 0;
     a.n_mtiles = (Mo + BM - 1) / BM;
     const long long n_slices = (R + SLICE - 1) / SLICE;
     a.n_items = n_slices * a.n_mtiles;
@@ -585,20 +755,20 @@ extern "C" UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const flo
     const size_t stg_bytes = (size_t)(4 + (No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS) * TN_PROD_WARPS * 32 * 16;
     const size_t budget = 227 * 1024 - 256 - 1024;
     const int stages = 2;                                                      // the MMAs of a chunk are short
-    int depth = (int)((budget - stages * stage_bytes) / stg_bytes);
-    if (depth > 6) depth = 6;
+    int depth = (int)((budget - stages * stage_bytes) / stg_bytes) / TN_GROUPS;    // staging slots per producer group
+    if (depth > 3) depth = 3;
     UBS_REQUIRE(depth >= 1, "ubs_tf32x3_gemm_tn: tiles do not fit shared memory");
     a.stages = stages; a.depth = depth; a.stage_stg_bytes = (int)stg_bytes;
     a.nbuf = 4 * No <= 512 ? 2 : 1;
     int cols = 32;
     while (cols < 2 * No * a.nbuf) cols *= 2;
     a.tmem_cols = cols;
-    const size_t smem = stages * stage_bytes + depth * stg_bytes + 256 + 1024;
+    const size_t smem = stages * stage_bytes + TN_GROUPS * depth * stg_bytes + 256 + 1024;
     UBS_OPT_IN_SMEM(tf32x3_gemm_tn_kernel, "ubs_tf32x3_gemm_tn");
     const int grid = (int)(a.n_items < ubs::kNumSMs ? a.n_items : ubs::kNumSMs);
     tf32x3_gemm_tn_kernel<<<grid, TN_THREADS, smem, (cudaStream_t)stream>>>(a);
     if (int rc = ubs::check_launch("ubs_tf32x3_gemm_tn")) return rc;
     const int P = Mo * No;
-    tn_reduce_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, n_slices, P, No, C, ldc);
+    tn_reduce_kernel<<<(P + RED_OUT - 1) / RED_OUT, RED_OUT * RED_WARPS, 0, (cudaStream_t)stream>>>(workspace, n_slices, P, No, C, ldc);
     return ubs::check_launch("ubs_tf32x3_gemm_tn(reduce)");
 }

@@ -722,7 +722,12 @@ def matmul_tn(a, b):
     """``a.T @ b``: the tcgen05 kernel for the long-reduction weight-gradient shapes, else the fp32 library GEMM."""
     if USE_TC_TN and a.is_cuda and a.shape[0] >= 4096 and b.shape[1] % 16 == 0 and 16 <= b.shape[1] <= 128 \
             and a.dtype == th.float32 and b.dtype == th.float32:
-        return tc_matmul_tn(a, b)
+        Mo = a.shape[1]
+        if Mo % 4 or a.stride(0) % 4 or a.stride(1) != 1:
+            # rows that are not 16-byte granular (the Q head: n_actions = 9) would take the kernel's scalar producer
+            # path: one small padded copy keeps the long reduction on the vector path
+            a = th.nn.functional.pad(a, (0, (-Mo) % 4))
+        return tc_matmul_tn(a, b)[:Mo]
     return a.t() @ b
 
 

@@ -51,4 +51,9 @@ if which in ("tn", "both"):
         us = timeit(lambda: ops.tc_matmul_tn(a, b))
         say(f"   rel err {err:.2e}  {us:.1f} us  {(R * Mo + R * No) * 4 / us / 1e3:.0f} GB/s")
         assert err < 2e-6
+if which == "tnbig":                      # one window-sized launch sequence, for ncu
+    a, b = th.randn(104448, 288, device=dev), th.randn(104448, 64, device=dev)
+    for _ in range(3):
+        ops.tc_matmul_tn(a, b)
+    th.cuda.synchronize()
 say("ok")

@@ -350,27 +350,97 @@ __device__ __forceinline__ void tn_stage(const ArgsTN& a, uint32_t stg, long lon
                           a.R, a.b_vec);
 }
 
-// Producer loop for 16-byte-aligned operands (the shapes of the BPTT window).  What a producer thread touches is fixed
-// by (warp, lane): 16 A columns (4 float4) and every 8th float4 column of B, row `lane` of every 32-row chunk.  With
-// the tile row m = warp * 16 + 4 j + e the swizzle term (m & 7) is a compile-time constant per (j, e), so the
-// K-major SWIZZLE_128B address of an element is  stage base + per-thread constant (8 of them, hoisted) + immediate:
-// ~7 instructions per element (5 to split, 2 stores) instead of re-deriving row clamps, 64-bit addresses and swizzles.
-// A columns past Mo are skipped altogether: they only feed accumulator rows the epilogue never reads.
-__device__ __forceinline__ void tn_produce_vec(const ArgsTN& a, char* sT, char* sStage, uint64_t* full, uint64_t* empty,
-                                               uint32_t stage_bytes, uint32_t b_tile, int grp, int warp, int lane) {
-    // grp: producer group (chunks grp, grp + TN_GROUPS, ...); warp: 0..7 within the group
+// ---- producer loop for 16-byte-aligned operands (the shapes of the BPTT window) --------------------------------------
+// Every shared-memory access below is explicit ld/st.shared on 32-bit addresses with immediate offsets: through generic
+// pointers the compiler re-derived the shared window (S2R SR_CgaCtaId) in front of each access and spilled.
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+// hi / lo TF32 halves of x to [bh + IMM_H] / [bl + IMM_L]
+template <int IMM_H, int IMM_L>
+__device__ __forceinline__ void st_hl(uint32_t bh, uint32_t bl, float x) {
+    const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float l = __uint_as_float((__float_as_uint(x - h) + 0x1000u) & 0xFFFFE000u);
+    asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(bh), "f"(h), "n"(IMM_H));
+    asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(bl), "f"(l), "n"(IMM_L));
+}
+// A tile rows m = 16 warp + 4 J + e of k-column `lane`: K-major SWIZZLE_128B offset = (m >> 3) * 1024 + (m & 7) * 128 +
+// ((lane >> 2) ^ (m & 7)) * 16 + (lane & 3) * 4; (m & 7) = (4 J + e) & 7 is a compile-time constant, so tA[k] = stage
+// base + 2048 warp + the per-thread swizzle term for k, and the rest is an immediate.  lo tile = hi tile + 16 KB.
+template <int J>
+__device__ __forceinline__ void tn_put_a(const float4& x, const uint32_t (&tA)[8]) {
+    constexpr int m = 4 * J;
+#define UBS_TN_A(E, V) st_hl<((m + E) >> 3) * 1024 + ((m + E) & 7) * 128, ((m + E) >> 3) * 1024 + ((m + E) & 7) * 128 + BM * 128>(tA[(m + E) & 7], tA[(m + E) & 7], V)
+    UBS_TN_A(0, x.x); UBS_TN_A(1, x.y); UBS_TN_A(2, x.z); UBS_TN_A(3, x.w);
+#undef UBS_TN_A
+}
+// B tile rows n = 4 (warp + 8 J) + e: 4 KB further per J; tBh[e] / tBl[e] carry everything else
+template <int J>
+__device__ __forceinline__ void tn_put_b(const float4& x, const uint32_t (&tBh)[4], const uint32_t (&tBl)[4]) {
+    st_hl<J * 4096, J * 4096>(tBh[0], tBl[0], x.x);
+    st_hl<J * 4096, J * 4096>(tBh[1], tBl[1], x.y);
+    st_hl<J * 4096, J * 4096>(tBh[2], tBl[2], x.z);
+    st_hl<J * 4096, J * 4096>(tBh[3], tBl[3], x.w);
+}
+
+struct TnCursor { uint32_t slot, kc, item, mt, sl; };        // position of a chunk stream: staging slot, (item, kc)
+
+// Coalesced 16-byte cp.async of chunk q into its staging slot: warp w copies rows w, w + 8, w + 16, w + 24 — 512
+// contiguous bytes of the A row (lane = float4 column) and the No floats of the B row (lanes < No / 4).  Rows past R
+// are zero-filled (src-size 0), A columns past Mo are skipped (never read back).
+__device__ __forceinline__ void tn_stage_vec(const ArgsTN& a, const TnCursor& q, uint32_t slot_addr, uint32_t PW, int warp, int lane) {
+    const long long row0 = (long long)q.sl * SLICE + q.kc * BK;
+    const int left = (int)(a.R - row0 < BK ? a.R - row0 : BK);      // rows of this chunk inside the matrix (may be <= 0)
+    const uint32_t dst = slot_addr + ((uint32_t)warp * PW + 4u * (uint32_t)lane) * 4u;
+    const bool a_on = (int)q.mt * BM + 4 * lane < a.Mo, b_on = 4 * lane < a.No;
+    const float* pa = a.A + (row0 + warp) * a.lda + ((int)q.mt * BM + 4 * lane);
+    const float* pb = a.B + (row0 + warp) * a.ldb + 4 * lane;
+    const long long sa = 8 * a.lda, sb = 8 * a.ldb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool ok = warp + 8 * i < left;
+        const int sz = ok ? 16 : 0;
+        const float* srca = pa + i * sa;
+        const float* srcb = pb + i * sb;
+        srca = ok ? srca : a.A;                                     // nothing is read when sz == 0; keep the address valid
+        srcb = ok ? srcb : a.B;
+        if (a_on)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 8u * PW * 4u), "l"(srca), "r"(sz) : "memory");
+        if (b_on)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 8u * PW * 4u + 512u), "l"(srcb), "r"(sz) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tn_cursor_next(TnCursor& q, uint32_t D, uint32_t n_mt) {
     constexpr int KC = SLICE / BK;
-    static_assert(KC % TN_GROUPS == 0, "a group keeps the same kc residue in every work item");
-    const int No = a.No, S = a.stages, D = a.depth;                 // D: staging slots of ONE group
+    q.slot = q.slot + 1 == D ? 0 : q.slot + 1;
+    q.kc += TN_GROUPS;
+    if (q.kc >= KC) { q.kc -= KC; q.item += gridDim.x; q.sl = q.item / n_mt; q.mt = q.item - q.sl * n_mt; }
+}
+
+// grp: producer group (chunks grp, grp + TN_GROUPS, ... of the CTA's chunk order; TN_GROUPS == stages == 2, so a group
+// owns one UMMA stage); warp: 0..7 within the group.  Per chunk: wait for the staged rows, read them back transposed
+// (thread = row `lane`; warp w = A columns 16 w .. 16 w + 15 and every 8th float4 column of B), refill the slot, then
+// split and store — ~7 instructions per element (5 to split, 2 stores) plus ~100 per chunk.
+__device__ __forceinline__ void tn_produce_vec(const ArgsTN& a, uint32_t sT, uint32_t sStage, uint64_t* full, uint64_t* empty,
+                                               uint32_t stage_bytes, uint32_t b_tile, int grp, int warp, int lane) {
+    constexpr int KC = SLICE / BK;
+    static_assert(KC % TN_GROUPS == 0 && TN_GROUPS == 2, "a group keeps its kc residue and owns UMMA stage grp (stages == 2)");
+    const int No = a.No;
+    const uint32_t D = (uint32_t)a.depth;                           // staging slots of ONE group
     const int nb4 = (No / 4 - warp + TN_PROD_WARPS - 1) / TN_PROD_WARPS;          // <= 4 (No <= 128)
     const uint32_t n_items = (uint32_t)a.n_items, n_mt = (uint32_t)a.n_mtiles;
     const uint32_t my_items = n_items > blockIdx.x ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t n_chunks = my_items * (KC / TN_GROUPS);          // chunks of this group
-    const uint32_t slots = 4 + (uint32_t)((No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS);
-    const uint32_t stg_stage = slots * TN_PROD_WARPS * 32 * 16;
-    const uint32_t tig = (uint32_t)(warp * 32 + lane);              // thread within the group
-    sStage += (size_t)grp * D * stg_stage;                          // this group's staging slots
-    const uint32_t stg0 = smem_u32(sStage) + tig * 16;
+    // staging slot: 32 rows x (128 A columns | No B columns | 4 pad) floats; the row pitch is 4 or 20 words mod 32, so
+    // the transposed float4 read-back (8 lanes = 8 rows per wavefront) is conflict-free
+    const uint32_t PW = 128u + (uint32_t)No + 4u;
+    const uint32_t stg_stage = (uint32_t)a.stage_stg_bytes;
+    const uint32_t stg_base = sStage + (uint32_t)grp * D * stg_stage;
+    const uint32_t rd_off = (uint32_t)lane * PW * 4u + (uint32_t)warp * 64u;      // row lane, A column 16 warp
     const uint32_t c = (uint32_t)lane >> 2, lane_off = ((uint32_t)lane & 3u) << 2;
     uint32_t preA[8], preB[4];
 #pragma unroll
@@ -379,108 +449,53 @@ __device__ __forceinline__ void tn_produce_vec(const ArgsTN& a, char* sT, char* 
 #pragma unroll
     for (int e = 0; e < 4; ++e)
         preB[e] = ((c ^ (kb0 + e)) << 4) + lane_off + (kb0 + e) * 128u + ((uint32_t)warp >> 1) * 1024u + 2u * BM * 128u;
+    const uint32_t bar_id = 1u + (uint32_t)grp;
 
-    // number of valid float4 A columns of this warp in m-tile mt: clamp((Mo - mt*128 - warp*16) / 4, 0, 4)
-    auto n_valid_a = [&](uint32_t mt) {
-        const int v = (a.Mo - (int)mt * BM - warp * 16) >> 2;
-        return v < 0 ? 0 : (v > 4 ? 4 : v);
-    };
-    // the staging stream (chunk g + D) and the consuming stream (chunk g) each carry their own (slot, kc, mt, slice)
-    // counters, advanced incrementally: one 32-bit division per 8 chunks instead of several per chunk
-    struct Cursor { uint32_t slot, kc, item, mt, sl; };
-    auto cursor_init = [&](Cursor& q) {
-        q.slot = 0; q.kc = (uint32_t)grp; q.item = blockIdx.x; q.sl = q.item / n_mt; q.mt = q.item - q.sl * n_mt;
-    };
-    auto cursor_next = [&](Cursor& q) {
-        q.slot = q.slot + 1 == (uint32_t)D ? 0 : q.slot + 1;
-        q.kc += TN_GROUPS;
-        if (q.kc >= KC) { q.kc -= KC; q.item += gridDim.x; q.sl = q.item / n_mt; q.mt = q.item - q.sl * n_mt; }
-    };
-    auto stage_chunk = [&](const Cursor& q) {
-        const long long row = (long long)q.sl * SLICE + q.kc * BK + lane;
-        const bool rowok = row < a.R;
-        const long long r = rowok ? row : a.R - 1;
-        const uint32_t dst = stg0 + q.slot * stg_stage;
-        const int na = n_valid_a(q.mt);
-        const float* pa = a.A + r * a.lda + (q.mt * BM + warp * 16);
-        const int sz = rowok ? 16 : 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < na)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(j * TN_PROD_WARPS * 32 * 16)), "l"(pa + 4 * j), "r"(sz) : "memory");
-        const float* pb = a.B + r * a.ldb + 4 * warp;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nb4)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)((4 + j) * TN_PROD_WARPS * 32 * 16)), "l"(pb + 4 * TN_PROD_WARPS * j), "r"(sz) : "memory");
-    };
-    auto split = [](float x, float& h, float& l) {
-        h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-        l = __uint_as_float((__float_as_uint(x - h) + 0x1000u) & 0xFFFFE000u);
-    };
-
-    Cursor qs, qc;                                                                   // staging / consuming
-    cursor_init(qs);
-    cursor_init(qc);
-    for (uint32_t g = 0; g < (uint32_t)D; ++g) {                                     // prologue: D chunks in flight
-        if (g < n_chunks) { stage_chunk(qs); cursor_next(qs); }
+    TnCursor qs, qc;                                                // staging / consuming stream
+    qs.slot = 0; qs.kc = (uint32_t)grp; qs.item = blockIdx.x; qs.sl = qs.item / n_mt; qs.mt = qs.item - qs.sl * n_mt;
+    qc = qs;
+    for (uint32_t g = 0; g < D; ++g) {                              // prologue: D chunks in flight
+        if (g < n_chunks) { tn_stage_vec(a, qs, stg_base + qs.slot * stg_stage, PW, warp, lane); tn_cursor_next(qs, D, n_mt); }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    const uint32_t st = sT + (uint32_t)grp * stage_bytes;           // this group's UMMA stage {A hi | A lo | B hi | B lo}
+    uint32_t tA[8], tBh[4], tBl[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tA[k] = st + preA[k];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { tBh[e] = st + preB[e]; tBl[e] = tBh[e] + b_tile; }
     for (uint32_t g = 0; g < n_chunks; ++g) {
-        const uint32_t gg = g * TN_GROUPS + (uint32_t)grp;                           // position in the CTA's chunk order
-        const uint32_t s = gg % (uint32_t)S, ph = (gg / (uint32_t)S) & 1u;           // its UMMA stage and phase
-        if (D == 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
-        else if (D == 5) asm volatile("cp.async.wait_group 4;" ::: "memory");
-        else if (D == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
-        else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (D >= 3) asm volatile("cp.async.wait_group 2;" ::: "memory");            // chunk g of this thread has landed ...
         else if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const int na = n_valid_a(qc.mt);
-        const char* stg = sStage + (size_t)qc.slot * stg_stage + (size_t)tig * 16;
-        float4 xa[4], xb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < na) xa[j] = *reinterpret_cast<const float4*>(stg + (size_t)(j * TN_PROD_WARPS * 32) * 16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nb4) xb[j] = *reinterpret_cast<const float4*>(stg + (size_t)((4 + j) * TN_PROD_WARPS * 32) * 16);
-        if (g + (uint32_t)D < n_chunks) { stage_chunk(qs); cursor_next(qs); }       // the slot is free again: refill it
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");                 // ... and everybody else's part of it
+        const int v = (a.Mo - (int)qc.mt * BM - warp * 16) >> 2;                    // valid float4 A columns of this warp
+        const int na = v < 0 ? 0 : (v > 4 ? 4 : v);
+        const uint32_t rd = stg_base + qc.slot * stg_stage + rd_off;
+        const uint32_t rdb = rd + 512u - 48u * (uint32_t)warp;                      // B column 4 warp: (128 + 4 warp) * 4 bytes
+        // A columns past Mo hold stale staging data: read them anyway (in range), they are not stored below
+        const float4 xa0 = lds128<0>(rd), xa1 = lds128<16>(rd), xa2 = lds128<32>(rd), xa3 = lds128<48>(rd);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xb0 = z4, xb1 = z4, xb2 = z4, xb3 = z4;
+        if (nb4 > 0) xb0 = lds128<0>(rdb);
+        if (nb4 > 1) xb1 = lds128<128>(rdb);
+        if (nb4 > 2) xb2 = lds128<256>(rdb);
+        if (nb4 > 3) xb3 = lds128<384>(rdb);
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");                 // the slot has been read: refill it
+        if (g + D < n_chunks) { tn_stage_vec(a, qs, stg_base + qs.slot * stg_stage, PW, warp, lane); tn_cursor_next(qs, D, n_mt); }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        cursor_next(qc);
-        mbar_wait(empty + s, ph ^ 1u);
-        char* st = sT + (size_t)s * stage_bytes;                   // {A hi 16 KB | A lo 16 KB | B hi | B lo}
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < na) {
-                const float v[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int mr = 4 * j + e, k = mr & 7;           // compile-time after unrolling
-                    float h, l;
-                    split(v[e], h, l);
-                    char* p = st + preA[k] + (mr >> 3) * 1024 + k * 128;
-                    *reinterpret_cast<float*>(p) = h;
-                    *reinterpret_cast<float*>(p + BM * 128) = l;
-                }
-            }
-        }
-        char* stb_lo = st + b_tile;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < nb4) {
-                const float v[4] = {xb[j].x, xb[j].y, xb[j].z, xb[j].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float h, l;
-                    split(v[e], h, l);
-                    *reinterpret_cast<float*>(st + preB[e] + j * 4096) = h;          // n = 4 (warp + 8 j) + e: 4 KB per j
-                    *reinterpret_cast<float*>(stb_lo + preB[e] + j * 4096) = l;
-                }
-            }
-        }
+        tn_cursor_next(qc, D, n_mt);
+        mbar_wait(empty + grp, (g & 1u) ^ 1u);                                      // stage grp, its g-th use
+        if (na > 0) tn_put_a<0>(xa0, tA);
+        if (na > 1) tn_put_a<1>(xa1, tA);
+        if (na > 2) tn_put_a<2>(xa2, tA);
+        if (na > 3) tn_put_a<3>(xa3, tA);
+        if (nb4 > 0) tn_put_b<0>(xb0, tBh, tBl);
+        if (nb4 > 1) tn_put_b<1>(xb1, tBh, tBl);
+        if (nb4 > 2) tn_put_b<2>(xb2, tBh, tBl);
+        if (nb4 > 3) tn_put_b<3>(xb3, tBh, tBl);
         fence_proxy_async();
-        mbar_arrive(full + s);
+        mbar_arrive(full + grp);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tf32x3_gemm_tn_kernel(const Arg
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < TN_EPI_WARP0 && a.a_vec && a.b_vec) {
-        tn_produce_vec(a, sT, sStage, full, empty, stage_bytes, b_tile, warp / TN_PROD_WARPS, warp % TN_PROD_WARPS, lane);
+        tn_produce_vec(a, smem_u32(sT), smem_u32(sStage), full, empty, stage_bytes, b_tile, warp / TN_PROD_WARPS, warp % TN_PROD_WARPS, lane);
     } else if (warp < TN_PROD_WARPS) {
         // ================================ producers (transposing split), any alignment ================================
         // warp w: 16 columns of the A tile and every 8th float4 column of the B tile; lane = row of the chunk.
@@ -752,9 +767,12 @@ extern "C" UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const flo
     const long long n_slices = (R + SLICE - 1) / SLICE;
     a.n_items = n_slices * a.n_mtiles;
     const size_t stage_bytes = 2 * BM * 128 + 2 * (size_t)No * 128;           // UMMA operand tiles of one chunk
-    const size_t stg_bytes = (size_t)(4 + (No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS) * TN_PROD_WARPS * 32 * 16;
+    // staging slot of one chunk: thread-private 16-byte slots (any-alignment path) or 32 padded rows (vector path)
+    const size_t stg_priv = (size_t)(4 + (No / 4 + TN_PROD_WARPS - 1) / TN_PROD_WARPS) * TN_PROD_WARPS * 32 * 16;
+    const size_t stg_rows = (size_t)BK * (BM + No + 4) * 4;
+    const size_t stg_bytes = stg_priv > stg_rows ? stg_priv : stg_rows;
     const size_t budget = 227 * 1024 - 256 - 1024;
-    const int stages = 2;                                                      // the MMAs of a chunk are short
+    const int stages = TN_GROUPS;                                              // one UMMA stage per producer group (the MMAs of a chunk are short)
     int depth = (int)((budget - stages * stage_bytes) / stg_bytes) / TN_GROUPS;    // staging slots per producer group
     if (depth > 3) depth = 3;
     UBS_REQUIRE(depth >= 1, "ubs_tf32x3_gemm_tn: tiles do not fit shared memory");

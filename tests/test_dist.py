@@ -129,3 +129,28 @@ def test_qmix_learner_stays_in_lockstep_across_ranks(tmp_path):
         assert th.allclose(a0, a1, rtol=0, atol=1e-7)
         moved = moved or not th.equal(a0, i0)
     assert moved
+
+
+def test_bucket_release_gather_equals_accumulating_into_the_views():
+    from uav_bs_ctrl_b200 import dist
+    th.manual_seed(0)
+    net = th.nn.Sequential(th.nn.Linear(5, 7), th.nn.ReLU(), th.nn.Linear(7, 3), th.nn.Linear(3, 2))
+    for p in net[3].parameters():
+        p.requires_grad_(True)
+    x = th.randn(11, 5)
+    b = dist.FlatGradBucket(net.parameters())
+    b.zero_()
+    net[:3](x).pow(2).sum().backward()                    # the last layer gets no gradient
+    b.rebind()
+    ref = b.flat.clone()
+    b.flat.fill_(7.0)
+    b.release()
+    assert all(p.grad is None for p in net.parameters())
+    net[:3](x).pow(2).sum().backward()
+    b.gather()
+    assert th.equal(b.flat, ref)
+    o = 0
+    for p in net.parameters():                            # .grad are views of the flat buffer again
+        assert p.grad.data_ptr() == b.flat.data_ptr() + 4 * o and th.equal(p.grad.flatten(), b.flat[o:o + p.numel()])
+        o += p.numel()
+    assert float(b.flat[-8:].abs().max()) == 0            # Linear(3, 2): 6 + 2 zeros

@@ -369,6 +369,7 @@ class GnnAgent(nn.Module):
         self._n_rounds = getattr(args, "n_rounds", 1)
         self._pack_cache = {}
         self._relpack_cache = None
+        self._param_gen = 0
         self.use_rel_act = True       # act step with the two observation relations folded into the act kernel (one launch)
         self.use_seq2 = True          # resident-weight sequence kernels when they fit (False: weight-streaming kernels)
         self.use_seq2_act = False     # act step through the resident-weight kernel (T = 1) instead of the streaming one
@@ -409,7 +410,7 @@ class GnnAgent(nn.Module):
         return d if d.supported() else None
 
     def _packed(self, dims, params):
-        key = tuple((t.data_ptr(), t._version) for t in params.values() if t is not None)
+        key = (self._param_gen,) + tuple((t.data_ptr(), t._version) for t in params.values() if t is not None)
         hit = self._pack_cache.get(dims.ints())
         if hit is None or hit[0] != key:
             buf = ops.agent_pack(dims, params, None if hit is None else hit[1])
@@ -423,7 +424,7 @@ class GnnAgent(nn.Module):
         convs = (self.enc.f_conv["seen"], self.enc.f_conv["near"])
         ps = [(c.fc_src.weight, c.fc_src.bias, c.fc_dst.weight, c.fc_dst.bias, c.attn, c.res_fc.weight, c.res_fc.bias)
               for c in convs]
-        key = tuple((t.data_ptr(), t._version) for p in ps for t in p)
+        key = (self._param_gen,) + tuple((t.data_ptr(), t._version) for p in ps for t in p)
         hit = self._relpack_cache
         if hit is None or hit[0] != key:
             c0 = convs[0]
@@ -439,6 +440,11 @@ class GnnAgent(nn.Module):
             return False
         L, c0 = arena.layout, self.enc.f_conv["seen"]
         return ops.agent_act_rel_supported(dims, c0._num_heads, L.F_gt, L.G, L.F_ubs, max(L.U - 1, 0), L.F_ag)
+
+    def mark_params_changed(self):
+        """For writers that do not bump ``Tensor._version`` (the fused multi-tensor AdamW kernel): the packed copies are
+        rebuilt at the next ``refresh_packed`` / act step."""
+        self._param_gen += 1
 
     def refresh_packed(self, arena=None):
         """Re-packs (in place) every act-step weight buffer built so far if a parameter changed since — a version check

@@ -58,6 +58,7 @@ class FlatGradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         n = sum(p.numel() for p in self.params)
         self.flat = th.zeros(n, dtype=dt, device=dev)
+        self._zeros = None
         o = 0
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
@@ -75,6 +76,28 @@ class FlatGradBucket:
                 if p.grad is not None:
                     g.copy_(p.grad)
                 p.grad = g
+            o += p.numel()
+
+    def release(self):
+        """Before ``backward()``: drop the views, so that autograd hands every parameter its gradient tensor instead of
+        launching one ``grad += g`` kernel per parameter into a zeroed bucket."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """After ``backward()``: ONE concatenation of the produced gradients into the flat buffer (zeros where a
+        parameter got none), then the parameters' ``.grad`` are the bucket views again."""
+        if self._zeros is None:
+            self._zeros = th.zeros_like(self.flat)
+        parts, o = [], 0
+        for p in self.params:
+            n = p.numel()
+            parts.append(self._zeros[o:o + n] if p.grad is None else p.grad.reshape(-1))
+            o += n
+        th.cat(parts, out=self.flat)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
 
     def all_reduce_mean(self):

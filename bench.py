@@ -235,6 +235,12 @@ def algorithmic_cost(name, meta):
     if name.startswith("tf32x3"):                       # C (M,N) = A (M,K) B (K,N): fp32 in / out, 3 TF32 MMAs per product
         M_, N_, K_ = meta
         return 4 * (M_ * K_ + K_ * N_ + M_ * N_), 2 * M_ * N_ * K_
+    if name == "colsum":                                # read once, C sums out
+        R_, C_ = meta
+        return 4 * (R_ * C_ + C_), R_ * C_
+    if name == "relu_bwd_colsum":                       # read dy and y, write dx, C sums out
+        R_, C_ = meta
+        return 4 * (3 * R_ * C_ + C_), 2 * R_ * C_
     if name == "agent_act_rel":
         # one-kernel act step: both star relations at capacity degree (cap rows per destination) + the agent step; the
         # relation outputs never leave the SM, so no xin traffic

@@ -152,6 +152,17 @@ UBS_API int64_t ubs_tf32x3_gemm_tn_workspace(int64_t R, int Mo, int No);
 UBS_API int ubs_tf32x3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                                float* workspace, int64_t R, int Mo, int No, void* stream);
 
+/* Bias gradients of the window: out[c] = sum over the R = T*N rows of X[r, c] — what autograd's `grad.sum(0)` computes
+ * for the biases of nn.Linear / GRUCell (reference algos/madrqn/agents/gnn_agents.py:65-67,101-107 run through
+ * learner.py:157 `loss.backward()`).  Streaming two-stage reduction in a fixed order (deterministic).  C % 4 == 0,
+ * C <= 1024, 16-byte aligned rows; workspace: ubs_colsum_workspace(C) floats.
+ * ubs_relu_bwd_colsum additionally applies the ReLU backward of the aggregator layer in the same pass:
+ * dX = X * (Y > 0) (dX may alias X), out = column sums of dX.                                                      */
+UBS_API int64_t ubs_colsum_workspace(int C);
+UBS_API int ubs_colsum(const float* X, int64_t ldx, int64_t R, int C, float* out, float* workspace, void* stream);
+UBS_API int ubs_relu_bwd_colsum(const float* X, int64_t ldx, const float* Y, int64_t ldy, float* dX, int64_t ldd,
+                                int64_t R, int C, float* out, float* workspace, void* stream);
+
 /* ---- TarMAC attention over block-diagonal comm graphs ----------------------------------------------------
  * Nodes are grouped in consecutive blocks of `block` (= agents per env, <= 32) nodes; every edge stays inside a
  * block (batched per-env graphs).  mask[v] bit i set  <=>  edge (block_start(v)+i) -> v exists.

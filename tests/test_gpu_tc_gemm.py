@@ -89,3 +89,34 @@ def test_matmul_tn_pads_rows_that_are_not_16_byte_granular():
     ops.TIMER = None
     assert "tf32x3_gemm_tn" in used and out.shape == (9, 64)
     assert_as_accurate(out, a.t() @ b, a.double().t() @ b.double(), what="padded gemm_tn", slack=4.0, floor_scale=2e-6)
+
+
+@pytest.mark.parametrize("R,C,ld", [(1, 4, 4), (300, 64, 64), (5000, 480, 480), (104448, 480, 480), (4097, 96, 352), (70000, 1024, 1024)])
+def test_colsum_matches_fp64(R, C, ld):
+    g = th.Generator().manual_seed(R + C)
+    big = th.randn(R, ld, generator=g).to(DEV)
+    x = big[:, ld - C:]                                   # row-strided view
+    ops.TIMER = ops.KernelTimer()
+    out = ops.colsum(x)
+    used = ops.TIMER.summary()
+    ops.TIMER = None
+    assert "colsum" in used
+    ref64 = x.double().sum(0)
+    assert_as_accurate(out, x.sum(0), ref64, what="colsum", slack=4.0, floor_scale=2e-6)
+    assert th.equal(out, ops.colsum(x))                   # fixed summation order
+
+
+def test_colsum_falls_back_for_rows_that_are_not_16_byte_granular():
+    x = th.randn(1000, 9, device=DEV)
+    assert th.allclose(ops.colsum(x), x.sum(0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("R,C", [(7, 64), (104448, 64), (5001, 128)])
+def test_relu_bwd_colsum_matches_torch(R, C):
+    g = th.Generator().manual_seed(R)
+    dy, y = th.randn(R, C, generator=g).to(DEV), th.randn(R, C, generator=g).relu().to(DEV)
+    ref = dy * (y > 0)
+    ref64 = ref.double().sum(0)
+    dx, cs = ops.relu_bwd_colsum_(dy.clone(), y)
+    assert th.equal(dx, ref)
+    assert_as_accurate(cs, ref.sum(0), ref64, what="relu_bwd colsum", slack=4.0, floor_scale=2e-6)

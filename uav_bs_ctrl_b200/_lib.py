@@ -48,6 +48,9 @@ _PROTOS = {
     "ubs_tf32x3_gemm": (C.c_int, [_F, _i64, _F, _i64, _F, _F, _i64, _i64, _int, _int, _int, _ptr]),
     "ubs_tf32x3_gemm_tn_workspace": (_i64, [_i64, _int, _int]),
     "ubs_tf32x3_gemm_tn": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _F, _i64, _int, _int, _ptr]),
+    "ubs_colsum_workspace": (_i64, [_int]),
+    "ubs_colsum": (C.c_int, [_F, _i64, _i64, _int, _F, _F, _ptr]),
+    "ubs_relu_bwd_colsum": (C.c_int, [_F, _i64, _F, _i64, _F, _i64, _i64, _int, _F, _F, _ptr]),
     "ubs_agent_seq2_smem_bytes": (_i64, [_int] * 6),
     "ubs_agent_seq2_fwd": (C.c_int, [_int] * 5 + [_F] * 13 + [_i64, _i64, _i64, _int, _ptr]),
     "ubs_agent_seq2_bwd": (C.c_int, [_int] * 5 + [_F] * 12 + [_i64, _i64, _int, _ptr]),

@@ -107,10 +107,15 @@ __device__ __forceinline__ void lds_row(const float* p, float (&x)[FS]) {
 // into HEADS groups of LPH = 32 / HEADS lanes: a group owns one head and walks the edges two per lane per pass
 // (80 edges = 5 full passes of an 8-lane group; no idle lanes at the BASELINE degree).  The tables are padded by one
 // float4 per head so that the groups' weight reads fall into different banks.
+#ifndef UBS_ACT_EPL
+#define UBS_ACT_EPL 5
+#endif
 template <int FS, int HEADS>
 __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, const float* tab, int D, float xv0, float xv1,
                                          int flags, float2* cbuf, float* out) {
-    constexpr int LPH = 32 / HEADS;
+    // EPL edges per lane per pass: the weight / destination operands of a channel (one LDS.128 + one LDS.64) are
+    // reused for all of them; 5 makes the BASELINE degree (80 edges over an 8-lane head group) exactly two passes
+    constexpr int LPH = 32 / HEADS, EPL = UBS_ACT_EPL;
     const int H = HEADS * D, Hp = H + HEADS, Dp = D + 1, lane = threadIdx.x & 31;
     const int k = lane / LPH, li = lane % LPH;
     const float4* wA = reinterpret_cast<const float4*>(tab);
@@ -131,11 +136,11 @@ __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, cons
     float m = -CUDART_INF_F, l = 0.f, acc[FS];
 #pragma unroll
     for (int f = 0; f < FS; ++f) acc[f] = 0.f;
-    for (int e = beg + li; e < end; e += 2 * LPH) {
-        float x[2][FS];
-        bool ok[2];
+    for (int e = beg + li; e < end; e += EPL * LPH) {
+        float x[EPL][FS];
+        bool ok[EPL];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < EPL; ++j) {
             const int ej = e + j * LPH;
             ok[j] = ej < end;
             if (ok[j]) lds_row<FS>(xs + ej * FS, x[j]);
@@ -144,9 +149,9 @@ __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, cons
                 for (int f = 0; f < FS; ++f) x[j][f] = 0.f;
             }
         }
-        float sc2[2];
+        float sc2[EPL];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < EPL; ++j) {
             sc2[j] = fmaf(pk.x, x[j][0], lin);
             if constexpr (FS > 1) sc2[j] = fmaf(pk.y, x[j][1], sc2[j]);
             if constexpr (FS > 2) sc2[j] = fmaf(pk.z, x[j][2], sc2[j]);
@@ -157,7 +162,7 @@ __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, cons
             const float4 w = wk[dd];
             const float2 c = ck[dd];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < EPL; ++j) {
                 float z = c.x;
                 z = fmaf(w.x, x[j][0], z);
                 if constexpr (FS > 1) z = fmaf(w.y, x[j][1], z);
@@ -167,7 +172,7 @@ __device__ __noinline__ void gat_rel_row(const float* xs, int beg, int end, cons
             }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < EPL; ++j) {
             if (ok[j]) {
                 const float mn = fmaxf(m, sc2[j]);
                 const float sc = __expf(m - mn);

@@ -718,6 +718,52 @@ def tc_matmul_tn(a, b, out=None):
     return out
 
 
+_COLSUM_WS = {}
+
+
+def _colsum_ok(x):
+    return (x.is_cuda and x.dtype == th.float32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 4 == 0
+            and 4 <= x.shape[1] <= 1024 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
+
+
+def _colsum_ws(x):
+    key = (x.device, th.cuda.current_stream().cuda_stream)
+    n = int(_lib.load().ubs_colsum_workspace(x.shape[1]))
+    ws = _COLSUM_WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = th.empty(n, dtype=th.float32, device=x.device)
+        _COLSUM_WS[key] = ws
+    return ws
+
+
+def colsum(x):
+    """``x.sum(0)`` of a (row-strided) ``(R, C)`` fp32 matrix: the bias gradients of a window (``ubs_colsum``, fixed
+    summation order).  Shapes outside the kernel (C % 4 != 0, unaligned rows) go to ``Tensor.sum``.  No autograd."""
+    if not _colsum_ok(x):
+        return x.sum(0)
+    lib = _lib.load()
+    out = th.empty(x.shape[1], dtype=th.float32, device=x.device)
+    with _timed("colsum", (x.shape[0], x.shape[1])):
+        _lib.check(lib.ubs_colsum(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _colsum_ws(x).data_ptr(),
+                                  _lib.stream()), "ubs_colsum")
+    return out
+
+
+def relu_bwd_colsum_(dy, y):
+    """In place ``dy *= (y > 0)`` and the column sums of the result, one pass (``ubs_relu_bwd_colsum``): ReLU backward
+    of the aggregator layer + its bias gradient.  Returns ``(dy, colsum)``.  No autograd."""
+    if not (_colsum_ok(dy) and _colsum_ok(y) and dy.shape == y.shape):
+        dy.mul_(y > 0)
+        return dy, dy.sum(0)
+    lib = _lib.load()
+    out = th.empty(dy.shape[1], dtype=th.float32, device=dy.device)
+    with _timed("relu_bwd_colsum", (dy.shape[0], dy.shape[1])):
+        _lib.check(lib.ubs_relu_bwd_colsum(dy.data_ptr(), dy.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), dy.stride(0),
+                                           dy.shape[0], dy.shape[1], out.data_ptr(), _colsum_ws(dy).data_ptr(), _lib.stream()),
+                   "ubs_relu_bwd_colsum")
+    return dy, out
+
+
 def matmul_tn(a, b):
     """``a.T @ b``: the tcgen05 kernel for the long-reduction weight-gradient shapes, else the fp32 library GEMM."""
     if USE_TC_TN and a.is_cuda and a.shape[0] >= 4096 and b.shape[1] % 16 == 0 and 16 <= b.shape[1] <= 128 \
@@ -907,7 +953,7 @@ class AgentSequence2(th.autograd.Function):
                        "ubs_agent_seq2_bwd")
         hprev = th.cat((h0.unsqueeze(0), h_out[:-1]), 0).view(TN, H)
         Sx, Sh = S[:, :H3 + Vp], S[:, H3:]                          # [dgi | dvsq] and [dvsq | dgh]
-        gb = S.sum(0)
+        gb = colsum(S)
         g = {"b_ih": gb[:H3], "b_hh": gb[H3 + Vp:]}
         g["W_out"], g["b_out"] = matmul_tn(dq2, h_out.view(TN, H)), dq2.sum(0)
         Gx = matmul_tn(Sx, x)                                       # (3H + Vp, H): [dW_ih[:, :H]; dW_vsq[:, :H]]
@@ -924,9 +970,9 @@ class AgentSequence2(th.autograd.Function):
         else:
             g["W_ih"] = Gx[:H3]
         if dims.aggr:
-            dpre = dx.mul_(x > 0)
+            dpre, g["b_aggr"] = relu_bwd_colsum_(dx, x)
             xg2 = xg.view(TN, dims.Fin)
-            g["W_aggr"], g["b_aggr"] = matmul_tn(dpre, xg2), dpre.sum(0)
+            g["W_aggr"] = matmul_tn(dpre, xg2)
             d_xg = dense(dpre, W.W_aggr_t).view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None
         else:
             d_xg = dx.view(T, N, dims.Fin) if ctx.needs_input_grad[0] else None

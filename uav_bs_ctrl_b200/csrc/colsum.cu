@@ -63,25 +63,28 @@ __global__ void __launch_bounds__(NT, 4) colsum_kernel(const Args a) {
     }
 }
 
-// out[c] = sum_p ws[p, c]: 8 warps take the partial rows p = w, w + 8, ...; combined in warp order
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, int nparts, int C, float* __restrict__ out) {
-    __shared__ float sm[8][32];
+// out[c] = sum_p ws[p, c]: a block owns 32 columns, its 32 warps take the partial rows p = w, w + 32, ... (8 independent
+// loads in flight per thread: a few dependent rounds for hundreds of partials), combined in warp order
+constexpr int FIN_WARPS = 32;
+__global__ void __launch_bounds__(32 * FIN_WARPS) colsum_final_kernel(const float* __restrict__ ws, int nparts, int C, float* __restrict__ out) {
+    __shared__ float sm[FIN_WARPS][32];
     const int lane = threadIdx.x % 32, w = threadIdx.x / 32, col = blockIdx.x * 32 + lane;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (col < C) {
-        int p = w;
-        for (; p + 24 < nparts; p += 32) {
+    float acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] += ws[(size_t)(p + 8 * u) * C + col];
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    if (col < C) {
+        for (int p = w; p < nparts; p += 8 * FIN_WARPS) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (p + u * FIN_WARPS < nparts) acc[u] += ws[(size_t)(p + u * FIN_WARPS) * C + col];
         }
-        for (int u = 0; p < nparts; p += 8, ++u) acc[u & 3] += ws[(size_t)p * C + col];
     }
-    sm[w][lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    sm[w][lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     __syncthreads();
     if (w == 0 && col < C) {
         float t = 0.f;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) t += sm[s][lane];
+        for (int s = 0; s < FIN_WARPS; ++s) t += sm[s][lane];
         out[col] = t;
     }
 }
@@ -110,7 +113,7 @@ static int launch(const float* X, long long ldx, const float* Y, long long ldy, 
     if (Y) colsum_kernel<true><<<grid, NT, 0, st>>>(a);
     else colsum_kernel<false><<<grid, NT, 0, st>>>(a);
     if (int rc = check_launch(what)) return rc;
-    colsum_final_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, grid, C, out);
+    colsum_final_kernel<<<(C + 31) / 32, 32 * FIN_WARPS, 0, st>>>(ws, grid, C, out);
     return check_launch(what);
 }
 

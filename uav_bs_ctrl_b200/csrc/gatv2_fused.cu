@@ -746,20 +746,29 @@ __global__ void __launch_bounds__(128) gatv2_bwd2_kernel(const GatArgs a) {
     for (int i = threadIdx.x; i < P; i += 128) a.partial[(size_t)blockIdx.x * P + i] = red[i];
 }
 
-// out[i] = sum_p partial[p*P + i], fixed order: 8 slices of parts per column, combined in slice order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int P,
-                                                              float* __restrict__ out) {
-    __shared__ float sm[8][32];
+// out[i] = sum_p partial[p*P + i], fixed order: 32 slices of parts per column (8 independent loads in flight per thread:
+// a few dependent rounds for ~600 partials), combined in slice order.
+constexpr int RED_SLICES = 32;
+__global__ void __launch_bounds__(32 * RED_SLICES) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int P,
+                                                                          float* __restrict__ out) {
+    __shared__ float sm[RED_SLICES][32];
     const int col = blockIdx.x * 32 + threadIdx.x % 32, slice = threadIdx.x / 32;
-    float acc = 0.f;
-    if (col < P)
-        for (int p = slice; p < nparts; p += 8) acc += partial[(size_t)p * P + col];
-    sm[slice][threadIdx.x % 32] = acc;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    if (col < P) {
+        for (int p = slice; p < nparts; p += 8 * RED_SLICES) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (p + u * RED_SLICES < nparts) acc[u] += partial[(size_t)(p + u * RED_SLICES) * P + col];
+        }
+    }
+    sm[slice][threadIdx.x % 32] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     __syncthreads();
     if (slice == 0 && col < P) {
         float t = 0.f;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) t += sm[s][threadIdx.x];
+        for (int s = 0; s < RED_SLICES; ++s) t += sm[s][threadIdx.x];
         out[col] = t;
     }
 }
@@ -990,6 +999,6 @@ extern "C" UBS_API int ubs_gatv2_seg_bwd_scores(const float* x_src, const float*
     int rc = 0;
     UBS_DISPATCH_FS_HEADS(ubs::launch_bwd, a, H, st)
     if (rc) return rc;
-    ubs::reduce_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(workspace, ubs::bwd_grid(n_dst), P, grad_params);
+    ubs::reduce_partials_kernel<<<(P + 31) / 32, 32 * ubs::RED_SLICES, 0, st>>>(workspace, ubs::bwd_grid(n_dst), P, grad_params);
     return ubs::check_launch("ubs_gatv2_bwd(reduce)");
 }

@@ -262,7 +262,13 @@ UBS_API int ubs_agent_act_uses_tma(int H, int M, int K, int A, int U, int Fin, i
  * ubs_gatv2_rel_pack ('seen' then 'near', ubs_gatv2_rel_pack_size floats each), rebuilt whenever a parameter of the
  * relation encoders changes.  packed / relpack / x_gt / x_ubs must be 16-byte aligned.
  * ubs_agent_act_rel_supported: 1 when the configuration fits the kernel (H = 32/64-class configs whose weights fit
- * 227 KB), else 0 — the caller then runs ubs_gatv2_seg_fwd x 2 + ubs_agent_act_fwd.                                   */
+ * 227 KB), else 0 — the caller then runs ubs_gatv2_seg_fwd x 2 + ubs_agent_act_fwd.
+ * gat_flags: UBS_GAT_* of the relation encoders, optionally | UBS_ACT_PDL: launch with programmatic stream
+ * serialization, so that inside a rollout (act, act, ... or act, env step, pack, act, ...) the grid's start-up — barrier
+ * init, the first weight layer's bulk copy — overlaps the tail of the previous kernel; the kernel reads the hidden
+ * state and the packet only after `griddepcontrol.wait`.  The caller guarantees that the kernel launched just before
+ * on the same stream does not write `packed` (i.e. never set it right after ubs_agent_pack).                          */
+#define UBS_ACT_PDL 0x100
 UBS_API int64_t ubs_gatv2_rel_pack_size(int heads, int D);
 UBS_API int ubs_gatv2_rel_pack(const float* W_src, const float* b_src, const float* W_dst, const float* b_dst,
                                const float* attn, const float* W_res, const float* b_res, int F_s, int F_d, int heads,

@@ -566,7 +566,7 @@ class GnnAgent(nn.Module):
         return self._run_sequence(dims, xin, h0.contiguous(), mask)
 
     @th.no_grad()
-    def arena_step(self, arena, t, q_out=None, explore=None):
+    def arena_step(self, arena, t, q_out=None, explore=None, pdl=False):
         """Inference on slot t: reads ``arena.h[t]``, writes ``arena.h[t+1]`` and the greedy actions ``arena.acts[t]``;
         returns the Q values.  Three launches (two relations + the fused step), no allocation-dependent host logic,
         so the call can be captured in a CUDA graph."""
@@ -578,7 +578,8 @@ class GnnAgent(nn.Module):
             ops.agent_act_rel(dims, self._packed(dims, self._fused_params()), self._relpacked(), arena.ptr("x_gt", t),
                               arena.ptr("ip_seen", t), L.F_gt, L.G, arena.ptr("x_ubs", t), arena.ptr("ip_near", t), L.F_ubs,
                               max(L.U - 1, 0), arena.ptr("x_agent", t), L.F_ag, c0._num_heads,
-                              ops.GAT_RESIDUAL | ops.GAT_RELU, arena.h[t], mask, arena.h[t + 1], q, arena.acts[t], explore)
+                              ops.GAT_RESIDUAL | ops.GAT_RELU | (ops.ACT_PDL if pdl else 0), arena.h[t], mask,
+                              arena.h[t + 1], q, arena.acts[t], explore)
             return q
         xin = self._arena_xin(arena, t, 1) if isinstance(self.enc, GraphObservationEncoder) else self._arena_flat_x(arena, t, 1)
         if self.use_seq2_act and self.use_seq2 and ops.seq2_supported(dims):

@@ -4,10 +4,11 @@ The reference keeps its replay as Python lists of per-step DGL graph objects on 
 re-batches them at every update (``algos/madrqn/buffer.py:7-42``, ``learner.py:99-116``).  Here one timestep of B
 env instances is ONE fixed-layout buffer of 4-byte words (a *packet*)
 
-    [ x_gt (N·G, F_gt) | x_ubs (N·(U-1), F_ubs) | x_agent (N, F_ag) | indptr_seen (N+1) | indptr_near (N+1) |
-      talk mask (N) | reward (N) | done (B) | bad_mask (B) ]            every section 16-byte aligned
+    [ x_agent (N, F_ag) | indptr_seen (N+1) | indptr_near (N+1) | talk mask (N) | reward (N) | done (B) | bad_mask (B) |
+      (state) | (flattened observations) | x_ubs (N·(U-1), F_ubs) | x_gt (N·G, F_gt) ]    every section on a 128-byte line
 
-so that (i) host → device staging of an observation is a single ``cudaMemcpyAsync`` from pinned memory, (ii) a
+so that (i) host → device staging of an observation is a single ``cudaMemcpyAsync`` from pinned memory of the packet's
+live prefix (fixed-size sections first, the ``seen`` rows last: rows past ``indptr_seen[-1]`` are never shipped), (ii) a
 *sequence arena* — ``(T+1)`` packets at a fixed stride in HBM plus the hidden states and actions — IS the replay
 entry, and (iii) the strided-segment kernels (``ubs_gatv2_seg_*``) encode all T+1 timesteps in one launch straight
 from the arena: no graph objects, no re-batching, no copies between ``act`` and ``update``.

@@ -405,6 +405,12 @@ __global__ void __launch_bounds__(NT, 1) agent_act_kernel(const StepArgs a) {
     const int n_valid = (int)min((int64_t)rpt, a.N - row0);
     const float scale = tm ? 1.0f / (float)K : 0.f;
     issue(0);
+    // Programmatic dependent launch (UBS_ACT_PDL; both instructions are no-ops in a normal launch): let the next grid of
+    // the stream start as soon as SMs free up, and do not touch anything the previous kernel may have written — the
+    // hidden state, the packet — before that kernel has completed and flushed.  Above this line: barrier init and the
+    // first weight layer's bulk copy (constant during a rollout).
+    pdl_trigger();
+    pdl_wait();
     load_tile(a.h0, row0, n_valid, H, H, sHp);
 
     for (int t = 0; t < a.T; ++t) {
@@ -619,7 +625,13 @@ int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled) {
     }
     const int rpt = a.d.rows_per_tile();
     const unsigned grid = (unsigned)((a.N + rpt - 1) / rpt);
-    act::agent_act_kernel<<<grid, act::NT, smem, st>>>(a);
+    // UBS_ACT_PDL: programmatic dependent launch — the grid may start while the previous kernel of the stream drains;
+    // everything it reads before pdl_wait() (the packed weights) must not be written by that kernel
+    const cudaError_t lrc = launch_pdl(act::agent_act_kernel, grid, (unsigned)act::NT, smem, st, a.pdl != 0, a);
+    if (lrc != cudaSuccess) {
+        set_error("ubs_agent_act_fwd: launch failed: %s", cudaGetErrorString(lrc));
+        return 1;
+    }
     *handled = true;
     return check_launch("ubs_agent_act_fwd(tma)");
 }
@@ -730,7 +742,8 @@ extern "C" UBS_API int ubs_agent_act_rel_fwd(int H, int M, int K, int A, int U, 
     UBS_REQUIRE(!a.d.tarmac() || mask, "ubs_agent_act_rel_fwd: TarMAC needs the block mask");
     UBS_REQUIRE(!a.d.tarmac() || n_rows % a.d.U == 0, "ubs_agent_act_rel_fwd: n_rows must be a multiple of agents per env");
     UBS_REQUIRE(eg_u == nullptr || (eg_a && eg_eps && actions), "ubs_agent_act_rel_fwd: incomplete epsilon-greedy arguments");
-    a.rel = mk_rel(relpack, x_gt, ip_seen, F_gt, cap_gt, x_ubs, ip_near, F_ubs, cap_ubs, x_agent, F_d, heads, gat_flags);
+    a.rel = mk_rel(relpack, x_gt, ip_seen, F_gt, cap_gt, x_ubs, ip_near, F_ubs, cap_ubs, x_agent, F_d, heads, gat_flags & ~UBS_ACT_PDL);
+    a.pdl = (gat_flags & UBS_ACT_PDL) ? 1 : 0;
     UBS_REQUIRE(ubs::agent_act_rel_fits(a.d, a.rel), "ubs_agent_act_rel_fwd: configuration outside the fused kernel "
                 "(ask ubs_agent_act_rel_supported first)");
     for (const void* p : {(const void*)packed, (const void*)relpack, (const void*)x_gt, (const void*)x_ubs})

@@ -100,6 +100,8 @@ struct StepArgs {
     float* st_dgh;         // (T, N, 3H)
     float* st_dvsq;        // (T, N, Vp)
     float* st_dpre;        // (T, N, H)   grad of the aggregator pre-activation
+    // launch option (host side): programmatic dependent launch of the act kernel (UBS_ACT_PDL)
+    int pdl;
 };
 
 int launch_agent_act(const StepArgs& a, cudaStream_t st, bool* handled);   // agent_act.cu

@@ -23,6 +23,28 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Kernel launch with (optionally) programmatic stream serialization: the grid may be scheduled while the previous kernel
+// of the stream is still draining.  Such a kernel executes `griddepcontrol.wait` (pdl_wait()) before it touches anything
+// the previous kernel may have written and `griddepcontrol.launch_dependents` (pdl_trigger()) as early as it likes;
+// both are no-ops in a normal launch.
+template <class Arg>
+inline cudaError_t launch_pdl(void (*kernel)(Arg), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                              const Arg& arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -37,7 +37,12 @@ struct StepArgs {
     int is_reset, profile;
 };
 
+// Both kernels trigger their dependents at once and read nothing before pdl_wait(): the act kernel that follows the pack
+// kernel inside a rollout graph is launched programmatically (UBS_ACT_PDL) and stages its first weight layer meanwhile.
+// (Launching these two programmatically as well was measured: no gain — 18.9 us per env step either way.)
 __global__ void __launch_bounds__(256) env_step_kernel(const __grid_constant__ StepArgs a) {
+    ubs::pdl_trigger();
+    ubs::pdl_wait();
     extern __shared__ double smem_d[];
     const ubs_env_cfg& c = a.cfg;
     Work w;
@@ -64,6 +69,8 @@ __global__ void __launch_bounds__(256) env_step_kernel(const __grid_constant__ S
 }
 
 __global__ void __launch_bounds__(128) env_pack_kernel(const __grid_constant__ StepArgs a) {
+    ubs::pdl_trigger();
+    ubs::pdl_wait();
     __shared__ int red[2][4];
     const ubs_env_cfg& c = a.cfg;
     const Scratch sc(c, a.B);
@@ -132,15 +139,16 @@ static int launch(const char* fn, const ubs_env_cfg* cfg, const ubs_env_state* s
     a.profile = env_profile;
     const size_t smem = Work::bytes(cfg->n_ubs, cfg->n_gts, cfg->n_rbs);
     UBS_REQUIRE(smem <= 227 * 1024, "%s: env working set (%zu B) exceeds shared memory", fn, smem);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = smem;
+    if (smem > 48 * 1024) {                      // opt in to the device maximum once per process (thread-safe static)
+        static const cudaError_t attr_rc = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        UBS_REQUIRE(attr_rc == cudaSuccess, "%s: cannot opt in to 227 KB of shared memory", fn);
     }
     cudaStream_t s = (cudaStream_t)stream;
-    env_step_kernel<<<(unsigned)B, 256, smem, s>>>(a);
+    cudaError_t e = ubs::launch_pdl(env_step_kernel, (unsigned)B, 256u, smem, s, false, a);
+    if (e != cudaSuccess) { ubs::set_error("%s: launch failed: %s", fn, cudaGetErrorString(e)); return 1; }
     if (int rc = ubs::check_launch(fn)) return rc;
-    env_pack_kernel<<<(unsigned)B, 128, 0, s>>>(a);
+    e = ubs::launch_pdl(env_pack_kernel, (unsigned)B, 128u, 0, s, false, a);
+    if (e != cudaSuccess) { ubs::set_error("%s: launch failed: %s", fn, cudaGetErrorString(e)); return 1; }
     return ubs::check_launch(fn);
 }
 

@@ -303,9 +303,10 @@ class MultiAgentQLearner:
         arena.explore_u.copy_(u.expand(-1, -1, self.n_agents).reshape(arena.S, -1))
         arena.explore_a.random_(0, self.n_actions)
 
-    def _act_arena_eager(self, arena, t):
-        # ε-greedy is fused into the step kernel: one uniform per env (explore_u holds it repeated for the env's agents)
-        return self.policy_net.arena_step(arena, t, explore=(arena.explore_u[t], arena.explore_a[t], self._eps_dev))
+    def _act_arena_eager(self, arena, t, pdl=False):
+        # ε-greedy is fused into the step kernel: one uniform per env (explore_u holds it repeated for the env's agents).
+        # pdl: inside a captured rollout the step may launch programmatically behind the previous kernel (UBS_ACT_PDL)
+        return self.policy_net.arena_step(arena, t, explore=(arena.explore_u[t], arena.explore_a[t], self._eps_dev), pdl=pdl)
 
     def act_arena(self, arena, t, eps_thres):
         """``act`` on arena slot t (observation already staged with ``arena.load``): writes ``arena.h[t+1]`` and the
@@ -372,9 +373,13 @@ class MultiAgentQLearner:
             raise ValueError(f"rollout_arena: max_seq_len ({T}) exceeds the env's episode_limit ({env.episode_limit})")
         self._set_eps(eps_thres)
 
-        def run():
+        use_pdl = bool(getattr(self.args, "act_pdl", True))
+
+        def run(captured=False):
             for t in range(T):
-                self._act_arena_eager(arena, t)
+                # inside the captured graph the packed weights are constant (refreshed before the replay) and the kernel
+                # ahead of step t >= 1 is the previous act step or the env's pack kernel: neither writes them
+                self._act_arena_eager(arena, t, pdl=captured and use_pdl and t > 0)
                 if env is not None:
                     env.step(arena, t)
 
@@ -400,7 +405,7 @@ class MultiAgentQLearner:
             g = th.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with th.cuda.graph(g):
-                run()
+                run(captured=True)
             g = (g, _lib.launch_count() - n0)
             graphs[key] = g
         g[0].replay()

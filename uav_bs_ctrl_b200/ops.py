@@ -10,6 +10,7 @@ import torch as th
 from . import _lib
 
 GAT_RESIDUAL, GAT_RELU = 1, 2
+ACT_PDL = 0x100            # ubs_agent_act_rel_fwd: programmatic dependent launch (include/ubs_gnn.h UBS_ACT_PDL)
 
 
 class KernelTimer:

@@ -432,9 +432,25 @@ class MultiAgentQLearner:
         # next_h = (1 - done) * next_h  (reference cache(), learner.py:90)
         keep = cat([(1 - a.sec("done", 1)).repeat_interleave(self.n_agents) for a in arenas], 0).unsqueeze(1)
         h0, h_targ = cat([a.h[0] for a in arenas], 0), cat([a.h[1] for a in arenas], 0) * keep
-        agent_out, _ = self.policy_net.arena_sequence(arenas, 0, T + 1, h0)
-        with th.no_grad():
-            target_out, _ = self.target_net.arena_sequence(arenas, 1, T, h_targ)
+        from . import ops
+        if h0.is_cuda and getattr(self.args, "overlap_target", True) and ops.TIMER is None:
+            # The target window (no grad) is independent of the policy window: run it on a second stream.  Its kernels
+            # interleave with the policy's on the SMs — the GATv2 kernels are FP32-issue bound, the recurrent window
+            # kernels tensor-pipe bound, the projections wait on HBM — instead of queueing behind them.
+            cur = th.cuda.current_stream()
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = th.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+            with th.cuda.stream(side), th.no_grad():
+                target_out, _ = self.target_net.arena_sequence(arenas, 1, T, h_targ)
+            agent_out, _ = self.policy_net.arena_sequence(arenas, 0, T + 1, h0)
+            cur.wait_stream(side)
+            target_out.record_stream(cur)             # allocated on the side stream, consumed (and freed) on this one
+        else:
+            agent_out, _ = self.policy_net.arena_sequence(arenas, 0, T + 1, h0)
+            with th.no_grad():
+                target_out, _ = self.target_net.arena_sequence(arenas, 1, T, h_targ)
         states = cat([a.states(T + 1) for a in arenas], 1) if self.mixer is not None else None
         loss, qvals = self._td_loss(agent_out, target_out, acts, rews, dones, states)
         return self._optimise(loss, qvals, sync)

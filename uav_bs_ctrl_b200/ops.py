@@ -5,6 +5,8 @@ caching allocator, and enqueues the kernels on the current CUDA stream.  CUDA te
 """
 from __future__ import annotations
 
+import os
+
 import torch as th
 
 from . import _lib
@@ -543,6 +545,8 @@ class AgentSequence(th.autograd.Function):
 # relation, every relation writing its own column block of ONE (rows, R*H) output buffer.
 _SIDE_STREAMS = {}
 SAVE_SCORES = True      # training forward keeps the per-(edge, head) attention scores for the backward (False: recompute)
+# SegmentEncode: the relations of one encode run on forked streams, forward and backward (UBS_FORK_RELATIONS=0: in order)
+FORK_RELATIONS = os.environ.get("UBS_FORK_RELATIONS", "1") != "0"
 
 
 def _side_stream(dev, i):
@@ -590,8 +594,9 @@ class SegmentEncode(th.autograd.Function):
         scores = [th.empty(n_seg * cap * heads, dtype=th.float32, device=dev) if (need_grad and SAVE_SCORES) else None
                   for cap in caps]
         ps = [_f32c(p.detach()) if p is not None else None for p in params]
-        # small launches (the act step) cannot fill the chip: relations run side by side on a forked stream
-        fork = R > 1 and rows <= 8192 and TIMER is None
+        # relations run side by side on a forked stream: small launches (the act step) cannot fill the chip, and in a
+        # window the short relation (`near`: 7 edges per destination, most lanes idle) fills issue slots the long one leaves
+        fork = R > 1 and FORK_RELATIONS and TIMER is None
         cur = th.cuda.current_stream()
         # forked: the side-stream relations (short: `near`) are enqueued first on a high-priority stream so that their
         # CTAs are resident next to the long relation's instead of queueing behind them
@@ -633,13 +638,23 @@ class SegmentEncode(th.autograd.Function):
         grad_out = _f32c(grad_out)
         it = iter(saved)
         ps = [next(it) if h else None for h in has]
-        grads = []
-        for r, sp in enumerate(specs):
+        fork = R > 1 and FORK_RELATIONS and TIMER is None
+        cur = th.cuda.current_stream()
+        bufs = []                                           # allocated on THIS stream, whichever stream fills them
+        for sp in specs:
+            bufs.append((th.empty(H * (sp.F_s + 2 * F_d + 4), dtype=th.float32, device=dev),
+                         th.empty(int(lib.ubs_gatv2_bwd_workspace(rows, sp.F_s, F_d, heads, D)), dtype=th.float32, device=dev)))
+        sides = []
+        for r in ((list(range(1, R)) + [0]) if fork else range(R)):
+            sp = specs[r]
             W = ps[7 * r:7 * r + 7]
-            Pn = H * (sp.F_s + 2 * F_d + 4)
-            gparams = th.empty(Pn, dtype=th.float32, device=dev)
-            ws = th.empty(int(lib.ubs_gatv2_bwd_workspace(rows, sp.F_s, F_d, heads, D)), dtype=th.float32, device=dev)
-            with _timed("gatv2_bwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, True)):
+            gparams, ws = bufs[r]
+            side = _side_stream(dev, r) if (fork and r > 0) else None
+            if side is not None:
+                side.wait_stream(cur)
+                sides.append(side)
+            with _timed("gatv2_bwd", (rows, sp.n_edges_hint, sp.F_s, F_d, heads, D, True)), \
+                    (th.cuda.stream(side) if side is not None else _nullctx()):
                 _lib.check(lib.ubs_gatv2_seg_bwd_scores(
                     sp.x_src_ptr, x_dst_ptr, sp.indptr_ptr, sp.src_idx_ptr, *[_lib.ptr(w) for w in W],
                     out.data_ptr() + 4 * r * H, grad_out.data_ptr() + 4 * r * H, _lib.ptr(stats[r, 0]),
@@ -647,7 +662,11 @@ class SegmentEncode(th.autograd.Function):
                     n_seg, n_dst_seg,
                     sp.n_edges_hint, sp.st_xsrc, st_xdst, sp.st_ip, sp.st_sidx, R * H, R * H, sp.F_s, F_d, heads, D,
                     slope, flags, _lib.stream()), "ubs_gatv2_seg_bwd")
-            o = 0
+        for side in sides:
+            cur.wait_stream(side)
+        grads = []
+        for r, sp in enumerate(specs):
+            gparams, o = bufs[r][0], 0
             for n, idx in ((H * sp.F_s, 0), (H, 1), (H * F_d, 2), (H, 3), (H, 4), (H * F_d, 5), (H, 6)):
                 k = 7 * r + idx
                 grads.append(gparams[o:o + n].view(shapes[k]) if has[k] else None)

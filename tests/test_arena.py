@@ -205,3 +205,35 @@ def test_replay_ring_keeps_the_order_of_the_reference_deque():
     with pytest.raises(ValueError):
         rp.sample(4)
     assert rp.nbytes() == 3 * (made[0].buf.numel() * 4 + made[0].h.numel() * 4 + made[0].acts.numel() * 8)
+
+
+@pytest.mark.gpu
+def test_stream_overlap_and_programmatic_launch_do_not_change_results():
+    """The update's second stream (target window), the forked relation streams and the programmatic launch of the act
+    steps inside the rollout graph only change WHEN kernels run: losses, gradients, hidden states and actions are
+    bit-identical to the in-order execution."""
+    from uav_bs_ctrl_b200 import ops
+    B, U, G, T = 64, 8, 80, 6
+    layout, pk = _episode(B, U, G, T, seed=90)
+    results = []
+    for overlap, fork, pdl in ((False, False, False), (True, True, True)):
+        L = _learner(B, U, T, graphs=True, seed=5)
+        L.args.overlap_target, L.args.act_pdl = overlap, pdl
+        old_fork, ops.FORK_RELATIONS = ops.FORK_RELATIONS, fork
+        try:
+            ar = L.new_arena(G)
+            outs = []
+            for cycle in range(2):                        # the second cycle replays the captured rollout graph
+                L.begin_sequence(ar)
+                for t in range(T + 1):
+                    ar.load(t, pk[t])
+                L.rollout_arena(None, ar, 0.0)
+                out = L.update_arena(ar, sync=False)
+                outs.append((ar.h.clone(), ar.acts.clone(), out["LossQ"].clone(), L.grad_bucket.flat.clone()))
+            th.cuda.synchronize()
+            results.append(outs)
+        finally:
+            ops.FORK_RELATIONS = old_fork
+    for a, b in zip(*results):
+        for x, y, what in zip(a, b, ("hidden states", "actions", "loss", "gradients")):
+            assert th.equal(x, y), what

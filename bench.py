@@ -291,6 +291,7 @@ def run_ours(a):
         learner.args.per_step_graphs = a.per_step_graphs
         learner.args.act_pdl = not a.no_pdl
         learner.args.overlap_target = not a.no_overlap
+        learner.args.update_graph = not a.no_update_graph
         learner.policy_net.use_seq2_act = a.act_seq2
         layout, packets = make_packets(B, T, a.profile, seed=1234 + 100 * rank, pin=True)
         h2d = sum(p.used_words() for p in packets) * 4        # what arena.load ships: header + the CSR rows in use
@@ -643,6 +644,7 @@ def main():
     ap.add_argument("--per-step-graphs", action="store_true",
                     help="value leg: one graph replay per vector-step (as the e2e leg must) instead of one per window")
     ap.add_argument("--act-seq2", action="store_true", help="act step through the resident-weight kernel (T=1) + small GEMMs")
+    ap.add_argument("--no-update-graph", action="store_true", help="update: eager launches instead of one CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="update: target window on the main stream (no second stream)")
     ap.add_argument("--no-pdl", action="store_true", help="rollout graph without programmatic dependent launch of the act steps")
     ap.add_argument("--no-e2e", action="store_true")

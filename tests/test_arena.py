@@ -213,7 +213,7 @@ def test_stream_overlap_and_programmatic_launch_do_not_change_results():
     steps inside the rollout graph only change WHEN kernels run: losses, gradients, hidden states and actions are
     bit-identical to the in-order execution."""
     from uav_bs_ctrl_b200 import ops
-    B, U, G, T = 64, 8, 80, 6
+    B, U, G, T = 256, 8, 40, 16                       # 2048 rows x 17 slots: above the size gates of both overlaps
     layout, pk = _episode(B, U, G, T, seed=90)
     results = []
     for overlap, fork, pdl in ((False, False, False), (True, True, True)):

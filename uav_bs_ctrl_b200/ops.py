@@ -573,6 +573,12 @@ class RelSpec:
         self.src_idx_ptr, self.st_sidx = src_idx_ptr, st_sidx
 
 
+def _fork_pays(rows):
+    """Act-step-sized launches cannot fill the chip and full windows are device-bound: forking helps both.  In between
+    (a 32-env window) the update is bound by the host enqueueing launches and the extra stream waits only cost."""
+    return rows <= 8192 or rows >= 32768
+
+
 class SegmentEncode(th.autograd.Function):
     """``forward(keepalive, specs, x_dst_ptr, st_xdst, F_d, n_seg, n_dst_seg, heads, D, slope, flags, *params)``
     with ``params`` = 7 tensors per relation ``(W_src, b_src, W_dst, b_dst, attn, W_res, b_res)``.
@@ -596,7 +602,7 @@ class SegmentEncode(th.autograd.Function):
         ps = [_f32c(p.detach()) if p is not None else None for p in params]
         # relations run side by side on a forked stream: small launches (the act step) cannot fill the chip, and in a
         # window the short relation (`near`: 7 edges per destination, most lanes idle) fills issue slots the long one leaves
-        fork = R > 1 and FORK_RELATIONS and TIMER is None
+        fork = R > 1 and FORK_RELATIONS and TIMER is None and _fork_pays(rows)
         cur = th.cuda.current_stream()
         # forked: the side-stream relations (short: `near`) are enqueued first on a high-priority stream so that their
         # CTAs are resident next to the long relation's instead of queueing behind them
@@ -638,7 +644,7 @@ class SegmentEncode(th.autograd.Function):
         grad_out = _f32c(grad_out)
         it = iter(saved)
         ps = [next(it) if h else None for h in has]
-        fork = R > 1 and FORK_RELATIONS and TIMER is None
+        fork = R > 1 and FORK_RELATIONS and TIMER is None and _fork_pays(rows)
         cur = th.cuda.current_stream()
         bufs = []                                           # allocated on THIS stream, whichever stream fills them
         for sp in specs:

@@ -430,8 +430,13 @@ class MultiAgentQLearner:
         windows, for the policy (with grad) and for the target network."""
         from . import ops
         arenas = list(arena) if isinstance(arena, (list, tuple)) else [arena]
+        # The update graph is enabled for the configuration family it has been validated on end to end — graph
+        # observation encoder with the one-kernel act step (exp3 shapes).  The MLP-observation configs (exp2) run their
+        # act steps through library GEMMs and torch ops whose per-step graphs, captured after the update graph, left it
+        # with a dangling address (illegal access on the next replay): they keep the eager update.
         if (len(arenas) == 1 and arenas[0].h.is_cuda and getattr(self.args, "cuda_graphs", False)
-                and getattr(self.args, "update_graph", True) and ops.TIMER is None):
+                and getattr(self.args, "update_graph", True) and ops.TIMER is None
+                and getattr(self.policy_net, "rel_act_supported", lambda a: False)(arenas[0])):
             out = self._update_arena_graphed(arenas[0], sync)
             if out is not None:
                 return out

@@ -237,3 +237,28 @@ def test_stream_overlap_and_programmatic_launch_do_not_change_results():
     for a, b in zip(*results):
         for x, y, what in zip(a, b, ("hidden states", "actions", "loss", "gradients")):
             assert th.equal(x, y), what
+
+
+@pytest.mark.gpu
+def test_graphed_update_follows_the_parameters_over_several_optimizer_steps():
+    """The update graph rebuilds every parameter-derived buffer (window weight layouts, packed weights) INSIDE the graph:
+    three consecutive updates through the replayed graph give the losses and parameters of three eager updates."""
+    B, U, G, T = 64, 8, 80, 6
+    layout, pk = _episode(B, U, G, T, seed=95)
+    runs = []
+    for graphed in (False, True):
+        L = _learner(B, U, T, graphs=True, seed=7)
+        L.args.update_graph = graphed
+        ar = L.new_arena(G)
+        L.begin_sequence(ar)
+        for t in range(T + 1):
+            ar.load(t, pk[t])
+        L.rollout_arena(None, ar, 0.0)
+        losses = [float(L.update_arena(ar, sync=True)["LossQ"]) for _ in range(3)]
+        runs.append((losses, [p.detach().clone() for p in L.policy_net.parameters()],
+                     [p.detach().clone() for p in L.target_net.parameters()]))
+    (l0, p0, t0), (l1, p1, t1) = runs
+    assert l0[0] != l0[1] != l0[2], "the parameters must move between the updates"
+    assert l0 == l1, (l0, l1)
+    for a, b in zip(p0 + t0, p1 + t1):
+        assert th.equal(a, b)

@@ -17,6 +17,7 @@ from __future__ import annotations
 import random
 import weakref
 from collections import deque
+import os
 from copy import deepcopy
 from typing import List
 
@@ -430,13 +431,11 @@ class MultiAgentQLearner:
         windows, for the policy (with grad) and for the target network."""
         from . import ops
         arenas = list(arena) if isinstance(arena, (list, tuple)) else [arena]
-        # The update graph is enabled for the configuration family it has been validated on end to end — graph
-        # observation encoder with the one-kernel act step (exp3 shapes).  The MLP-observation configs (exp2) run their
-        # act steps through library GEMMs and torch ops whose per-step graphs, captured after the update graph, left it
-        # with a dangling address (illegal access on the next replay): they keep the eager update.
+        # one arena, fixed addresses: the update replays as a CUDA graph (UBS_UPDATE_GRAPH=0 or args.update_graph = False:
+        # eager launches)
         if (len(arenas) == 1 and arenas[0].h.is_cuda and getattr(self.args, "cuda_graphs", False)
                 and getattr(self.args, "update_graph", True) and ops.TIMER is None
-                and getattr(self.policy_net, "rel_act_supported", lambda a: False)(arenas[0])):
+                and os.environ.get("UBS_UPDATE_GRAPH", "1") != "0"):
             out = self._update_arena_graphed(arenas[0], sync)
             if out is not None:
                 return out
@@ -465,6 +464,10 @@ class MultiAgentQLearner:
                     del loss, qvals                         # nothing of the warm-up's autograd graph survives into the capture
                 cur.wait_stream(side)
                 th.cuda.synchronize()
+                # Everything derived from the parameters (window weight layouts, packed weights) must be REBUILT INSIDE the
+                # capture: a cache hit here would bake the warm-up's buffers — stale after the first optimizer step, and
+                # freed below — into the graph.
+                self._invalidate_derived_weights()
                 g = th.cuda.CUDAGraph()
                 n0 = _lib.launch_count()
                 if getattr(self, "_update_pool", None) is None:
@@ -483,10 +486,7 @@ class MultiAgentQLearner:
                 ent = None
             finally:
                 # derived-weight caches filled during the capture hold buffers whose contents only exist after a replay
-                ops._SEQ2_CACHE.clear()
-                for net in (self.policy_net, self.target_net):
-                    if hasattr(net, "mark_params_changed"):
-                        net.mark_params_changed()
+                self._invalidate_derived_weights()
             if ent is None:
                 return None
             graphs["update"] = ent
@@ -494,6 +494,13 @@ class MultiAgentQLearner:
         _lib.add_launches(ent[1])
         # the graph's outputs live at fixed addresses that the next replay overwrites: hand out copies
         return self._apply_gradients(ent[2].detach().clone(), ent[3].detach().clone(), sync)
+
+    def _invalidate_derived_weights(self):
+        from . import ops
+        ops._SEQ2_CACHE.clear()
+        for net in (self.policy_net, self.target_net):
+            if hasattr(net, "mark_params_changed"):
+                net.mark_params_changed()
 
     def _arena_loss(self, arenas):
         """TD loss of the window(s): policy window with grad, target window without (reference ``learner.py:118-154``)."""
